@@ -1,0 +1,172 @@
+/* morpho_cuda.h — C ABI of libmorpho_cuda.so ("libmorpho-cuda").
+ *
+ * The B200-native implementation of ONE hot path of Morpho (Morpho-lang/morpho
+ * 0.6.4): the per-element integrand / total / gradient / fieldgradient maps of
+ * the geometric functionals and the scatter of per-element gradients into the
+ * vertex-gradient Matrix.  Plain pointers and sizes only; no Morpho, torch or
+ * C++ types cross this boundary.  All entry points return an int status
+ * (MCU_OK == 0); no exception or longjmp crosses the ABI.  The library is
+ * single-caller (Morpho builtins run on the interpreter thread, one call at a
+ * time per VM: src/builtin/builtin.h:54, src/core/vm.c:1300-1308) and owns its
+ * CUDA stream.  There is NO CPU fallback: every compute entry point fails with
+ * MCU_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Each entry point cites the reference interface it replaces.  The
+ * reference-side binding (a Morpho extension that patches the builtin method
+ * tables) is morpho_b200/ext/morphocuda.c; see INTEGRATION.md.
+ *
+ * Data layouts are the reference's own:
+ *   vertices : double[nv*dim], vertex i at [i*dim .. i*dim+dim)   (matrix.h:59-73)
+ *   elements : int[nel*(g+1)], ids ascending inside an element    (sparse.c:505-510)
+ *   gradient : double[nv*dim] same layout as vertices, zero where untouched
+ *   integrand: double[nel]    (1 x nel Matrix), zero for unselected elements
+ *   field    : double[nv*psize], vertex i at [i*psize ..)         (field.c:419-434)
+ */
+#ifndef MORPHO_CUDA_H
+#define MORPHO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCU_ABI_VERSION 1
+
+/* ---- status codes; mcu_error_id() maps them to the reference's error ids ---- */
+enum {
+    MCU_OK = 0,
+    MCU_ERR_ARGS = 1,        /* bad argument combination → "FnctlArgs" / "FnctlIntMsh" (functional.h:97-120) */
+    MCU_ERR_ELNOTFOUND = 2,  /* "FnctlELNtFnd": mesh has no elements of that grade (functional.c:115-129) */
+    MCU_ERR_DEGENERATE = 3,  /* an element gradient returned false → method result is nil (functional.c:392,412-415) */
+    MCU_ERR_VOLENCLZERO = 4, /* "VolEnclZero" (functional.c:2148-2151) */
+    MCU_ERR_UNSUPPORTED = 5, /* functional/mode not accelerated: caller keeps the reference builtin */
+    MCU_ERR_CUDA = 6,        /* CUDA runtime failure or no usable device */
+    MCU_ERR_ALLOC = 7        /* "Alloc" */
+};
+
+/* ---- functional classes (functional.c:6260-6280); numbering shared with the oracle ---- */
+enum {
+    MCU_F_LENGTH = 1,          /* functional.c:1948-1993 */
+    MCU_F_AREAENCLOSED = 2,    /* functional.c:2000-2056 */
+    MCU_F_AREA = 3,            /* functional.c:2063-2124 */
+    MCU_F_VOLUMEENCLOSED = 4,  /* functional.c:2131-2178 */
+    MCU_F_VOLUME = 5,          /* functional.c:2185-2246 */
+    MCU_F_LINECURVATURESQ = 6, /* functional.c:2940-3058 */
+    MCU_F_GRADSQ = 7,          /* functional.c:3485-3732 */
+    MCU_F_NORMSQ = 8,          /* functional.c:4149-4194 */
+    MCU_F_NEMATIC = 9,         /* functional.c:3750-3984 */
+    MCU_F_NEMATICELECTRIC = 10 /* functional.c:3996-4142 */
+};
+
+/* ---- evaluation modes = the builtin method names (functional.h:55-60) ---- */
+enum {
+    MCU_TOTAL = 0,         /* .total()         → 1 double                         */
+    MCU_INTEGRAND = 1,     /* .integrand()     → nel doubles                      */
+    MCU_GRADIENT = 2,      /* .gradient()      → nv*dim doubles                   */
+    MCU_FIELDGRADIENT = 3  /* .fieldgradient() → nv*psize doubles                 */
+};
+
+/* ---- gradient assembly strategies (mcu_set_option("gradient_path", …)) ---- */
+enum {
+    MCU_PATH_AUTO = 0,
+    MCU_PATH_GATHER = 1,   /* CSR-transpose vertex gather, reference summation order */
+    MCU_PATH_PATCH = 2     /* shared-memory patch kernel (triangles; analytic gradients) */
+};
+
+typedef struct mcu_mesh mcu_mesh;           /* device mirror of objectmesh      (mesh.h:25-31)      */
+typedef struct mcu_field mcu_field;         /* device mirror of objectfield     (field.h:25-41)     */
+typedef struct mcu_selection mcu_selection; /* device mirror of objectselection (selection.h:22-31) */
+
+/* Call descriptor: the part of functional_mapinfo (functional.h:226-241) plus the
+ * per-class reference structs (curvatureref functional.c:2935-2939, fieldref 3436-3439,
+ * nematicref 3743-3748, nematicelectricref 3996-4000) that the element maps read. */
+typedef struct mcu_functional {
+    int functional;      /* MCU_F_*                                                    */
+    int grade;           /* <=0: class default (GradSq/Nematic*: mesh max grade)       */
+    double ksplay, ktwist, kbend, pitch; /* Nematic (functional.c:3757-3791)            */
+    int haspitch;
+    int integrandonly;   /* LineCurvatureSq (functional.c:2956-2958)                   */
+    mcu_field *field[2]; /* [0] director / q ; [1] electric potential (scalar)         */
+    int wrt;             /* MCU_FIELDGRADIENT: which of field[] is differentiated      */
+} mcu_functional;
+
+/* ---- library lifetime (replaces nothing: extension _initialize/_finalize, extensions.c:134-154) ---- */
+int mcu_abi_version(void);
+int mcu_init(int device);                   /* select device, create the stream; idempotent */
+int mcu_finalize(void);
+const char *mcu_last_error(void);           /* human readable text of the last failure */
+const char *mcu_error_id(int status);       /* Morpho error id ("VolEnclZero", …) or "" */
+int mcu_set_option(const char *key, long value);
+long mcu_get_option(const char *key);
+int mcu_sync(void);                         /* wait for the library stream */
+int mcu_set_stream(void *cuda_stream);      /* adopt a caller-owned cudaStream_t (NULL → own stream) */
+
+/* ---- Mesh mirror: object_newmesh (mesh.c:74), Mesh.setvertexmatrix (mesh.c:1145-1160),
+ *      mesh_getconnectivityelement(m,0,g) (mesh.c:296-307) ---- */
+mcu_mesh *mcu_mesh_create(int dim, int nv);
+int mcu_mesh_destroy(mcu_mesh *m);
+int mcu_mesh_set_vertices(mcu_mesh *m, const double *host_vert);      /* H2D of the whole vertex matrix */
+int mcu_mesh_set_vertices_device(mcu_mesh *m, const double *dev_vert); /* D2D */
+int mcu_mesh_get_vertices(mcu_mesh *m, double *host_vert);            /* D2H */
+double *mcu_mesh_vertices_device(mcu_mesh *m);                        /* device pointer of the mirror */
+int mcu_mesh_set_connectivity(mcu_mesh *m, int grade, int nel, const int *host_rix);
+int mcu_mesh_counts(const mcu_mesh *m, int *dim, int *nv, int nel[4]);
+/* vertex→element incidence as the reference builds it with sparse_transpose → cs_transpose
+ * (sparse.c:1227-1244, mesh.c:663-685): tptr[nv+1], tidx[nel*(g+1)] element ids ascending per vertex. */
+int mcu_mesh_get_transpose(mcu_mesh *m, int grade, int *host_tptr, int *host_tidx);
+
+/* ---- Field mirror (vertex based, P1): object_newfield (field.c:107-170) ---- */
+mcu_field *mcu_field_create(mcu_mesh *m, int psize);
+int mcu_field_destroy(mcu_field *f);
+int mcu_field_set(mcu_field *f, const double *host_data);
+int mcu_field_set_device(mcu_field *f, const double *dev_data);
+int mcu_field_get(mcu_field *f, double *host_data);
+double *mcu_field_device(mcu_field *f);
+
+/* ---- Selection mirror: element ids of one grade (selection.h:22-31; the integer keys of
+ *      sel->selected[g], functional.c:226-229). Order of ids is irrelevant to the result set. ---- */
+mcu_selection *mcu_selection_create(mcu_mesh *m, int grade, int n, const int *host_ids);
+int mcu_selection_destroy(mcu_selection *s);
+int mcu_selection_get_ids(mcu_selection *s, int *host_ids_sorted, int cap); /* returns count */
+
+/* ---- Evaluation = functional_sumintegrand / functional_mapintegrand / functional_mapgradient /
+ *      functional_mapnumericalgradient / functional_mapnumericalfieldgradient
+ *      (functional.c:962-996, 1049-1085, 1092-1135, 1193-1247, 1428-1503).
+ *      mcu_eval copies the result to host memory (the objectmatrix / objectfield the builtin
+ *      returns); mcu_eval_device leaves it in device memory and does not synchronise. ---- */
+int mcu_eval(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *host_out);
+int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *dev_out);
+/* number of doubles `mode` produces for this functional on this mesh */
+long mcu_result_size(mcu_mesh *m, const mcu_functional *f, int mode);
+
+/* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.
+ *      kind 0: Coulomb f=1/r, f'=-1/r^2 (examples/thomson/thomson.morpho:26).
+ *      mode MCU_TOTAL / MCU_INTEGRAND (n doubles) / MCU_GRADIENT (n*dim doubles). ---- */
+int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *params, double cutoff,
+                 int mode, double *host_out);
+int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff,
+                        int mode, double *dev_out);
+
+/* ---- element partition across GPUs: functional_binbounds (functional.c:863-879) ---- */
+int mcu_binbounds(int nel, int nbins, int *bounds);
+
+/* ---- measurement helpers (bench.py): CUDA events on the library stream ---- */
+int mcu_timer_start(void);
+int mcu_timer_stop(float *ms);
+long mcu_launch_count(void);                /* kernels launched by this library since mcu_init */
+int mcu_device_malloc(void **ptr, size_t bytes);
+int mcu_device_free(void *ptr);
+int mcu_flush_l2(void);                     /* overwrite a > L2-sized scratch buffer */
+
+/* ---- introspection of the patch planner (pure host code, no CUDA call): used by the CPU tests
+ *      of the host logic.  counts = {patches, vertex-list entries, packed triangles, colour
+ *      offsets, max colours, ints per header}. Output arrays may be NULL. ---- */
+int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, long counts[6],
+                         int *hdr_out, int *vtx_out, unsigned *elems_out, int *elem_ids_out, int *color_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORPHO_CUDA_H */

@@ -1,0 +1,214 @@
+"""The functional classes of the accelerated path, with the reference's method names.
+
+Each class mirrors a builtin class registered in functional.c:6260-6280 and offers
+``total`` / ``integrand`` / ``gradient`` (/ ``fieldgradient``) with the reference's argument
+convention: a Mesh, an optional Selection and an optional Field, in any order
+(functional_validateargs, functional.c:82-102).  Results are numpy arrays in the reference
+layouts.  A degenerate element makes ``gradient`` return ``None``
+— the reference returns nil there (functional.c:392,412-415) — and named errors are raised
+as :class:`MorphoError` with the reference's error id.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MCU_FIELDGRADIENT, MCU_GRADIENT, MCU_INTEGRAND, MCU_TOTAL, FUNCTIONAL_IDS, McuFunctional,
+                   MorphoError, check, lib)
+from .geometry import Field, Mesh, Selection
+
+__all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq",
+           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential"]
+
+
+class Functional:
+    name = None
+    grade = -1
+
+    def __init__(self):
+        self.fields = []
+
+    # -- descriptor ------------------------------------------------------------
+    def _desc(self, wrt=0):
+        d = McuFunctional()
+        d.functional = FUNCTIONAL_IDS[self.name]
+        d.grade = int(getattr(self, "grade", -1) or -1)
+        d.ksplay = float(getattr(self, "ksplay", 1.0))
+        d.ktwist = float(getattr(self, "ktwist", 1.0))
+        d.kbend = float(getattr(self, "kbend", 1.0))
+        pitch = getattr(self, "pitch", None)
+        d.pitch = 0.0 if pitch is None else float(pitch)
+        d.haspitch = 0 if pitch is None else 1
+        d.integrandonly = int(bool(getattr(self, "integrandonly", False)))
+        for i, f in enumerate(self.fields[:2]):
+            d.field[i] = f._h
+        d.wrt = wrt
+        return d
+
+    @staticmethod
+    def _args(args):
+        """functional_validateargs (functional.c:82-102)."""
+        mesh = sel = fld = None
+        for a in args:
+            if isinstance(a, Mesh):
+                mesh = a
+            elif isinstance(a, Selection):
+                sel = a
+            elif isinstance(a, Field):
+                fld = a
+                mesh = a.mesh
+        if mesh is None:
+            raise MorphoError(_lib.MCU_ERR_ARGS, "FnctlIntMsh", "Method 'integrand' requires a mesh as the argument.")
+        return mesh, sel, fld
+
+    def _loop_grade(self, mesh):
+        if self.name in ("GradSq", "Nematic", "NematicElectric"):
+            g = int(getattr(self, "grade", -1) or -1)
+            return g if g > 0 else mesh.maxgrade()
+        return {"Length": 1, "AreaEnclosed": 1, "Area": 2, "VolumeEnclosed": 2, "Volume": 3,
+                "LineCurvatureSq": 0, "NormSq": 0}[self.name]
+
+    def _eval(self, mode, args, wrt=0):
+        mesh, sel, fld = self._args(args)
+        d = self._desc(wrt)
+        L = lib()
+        n = L.mcu_result_size(mesh._h, C.byref(d), mode)
+        g = self._loop_grade(mesh)
+        if n < 0:
+            if g > 0 and mesh.count(g) == 0 and g not in mesh._conn:
+                raise MorphoError(_lib.MCU_ERR_ELNOTFOUND, "FnctlELNtFnd", f"Mesh does not provide elements of grade {g}.")
+            check(_lib.MCU_ERR_ARGS)
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        hsel = sel._handle(g) if sel is not None else None
+        rc = L.mcu_eval(mesh._h, C.byref(d), hsel, mode, out.ctypes.data)
+        if rc == _lib.MCU_ERR_DEGENERATE:
+            return None            # nil, as the reference (functional.c:412-415)
+        check(rc)
+        return out[:n]
+
+    # -- the builtin methods (functional.h:55-60) --------------------------------
+    def total(self, *args):
+        r = self._eval(MCU_TOTAL, args)
+        return None if r is None else float(r[0])
+
+    def integrand(self, *args):
+        return self._eval(MCU_INTEGRAND, args)
+
+    def gradient(self, *args):
+        mesh, _, _ = self._args(args)
+        r = self._eval(MCU_GRADIENT, args)
+        return None if r is None else r.reshape(mesh.nv, mesh.dim)
+
+
+class Length(Functional):
+    name = "Length"
+
+
+class AreaEnclosed(Functional):
+    name = "AreaEnclosed"
+
+
+class Area(Functional):
+    name = "Area"
+
+
+class VolumeEnclosed(Functional):
+    name = "VolumeEnclosed"
+
+
+class Volume(Functional):
+    name = "Volume"
+
+
+class LineCurvatureSq(Functional):
+    name = "LineCurvatureSq"
+
+    def __init__(self, integrandonly=False):
+        super().__init__()
+        self.integrandonly = integrandonly
+
+
+class _FieldFunctional(Functional):
+    def fieldgradient(self, *args):
+        mesh, sel, fld = self._args(args)
+        wrt = 0
+        if fld is not None and len(self.fields) > 1 and fld is self.fields[1]:
+            wrt = 1
+        r = self._eval(MCU_FIELDGRADIENT, args, wrt)
+        if r is None:
+            return None
+        return r.reshape(mesh.nv, self.fields[wrt].psize)
+
+
+class GradSq(_FieldFunctional):
+    name = "GradSq"
+
+    def __init__(self, field, grade=None):
+        super().__init__()
+        if not isinstance(field, Field):
+            raise MorphoError(_lib.MCU_ERR_ARGS, "InvldArgs", "GradSq requires a field")
+        self.fields = [field]
+        self.grade = grade if grade else -1
+
+
+class NormSq(_FieldFunctional):
+    name = "NormSq"
+
+    def __init__(self, field):
+        super().__init__()
+        if not isinstance(field, Field):
+            raise MorphoError(_lib.MCU_ERR_ARGS, "InvldArgs", "NormSq requires a field")
+        self.fields = [field]
+
+
+class Nematic(_FieldFunctional):
+    name = "Nematic"
+
+    def __init__(self, field, ksplay=1.0, ktwist=1.0, kbend=1.0, pitch=None, grade=None):
+        super().__init__()
+        if not isinstance(field, Field):
+            raise MorphoError(_lib.MCU_ERR_ARGS, "NmtcArgs", "Nematic requires a field as its argument.")
+        self.fields = [field]
+        self.ksplay, self.ktwist, self.kbend, self.pitch = ksplay, ktwist, kbend, pitch
+        self.grade = grade if grade else -1
+
+
+class NematicElectric(_FieldFunctional):
+    name = "NematicElectric"
+
+    def __init__(self, director, potential, grade=None):
+        super().__init__()
+        if not (isinstance(director, Field) and isinstance(potential, Field)):
+            raise MorphoError(_lib.MCU_ERR_ARGS, "FnctlArgs", "NematicElectric requires two fields")
+        self.fields = [director, potential]
+        self.grade = grade if grade else -1
+
+
+class PairwisePotential:
+    """All-pairs potential on the mesh vertices (modules/functionals.morpho:87-141).
+
+    Only closures the device knows can be accelerated; ``kind="coulomb"`` is
+    f(r) = 1/r, f'(r) = -1/r^2, the pair used by examples/thomson/thomson.morpho:26.
+    """
+
+    def __init__(self, kind="coulomb", cutoff=None):
+        if kind != "coulomb":
+            raise MorphoError(_lib.MCU_ERR_UNSUPPORTED, "", f"pairwise kind '{kind}' is not accelerated")
+        self.kind, self.cutoff = 0, (0.0 if cutoff is None else float(cutoff))
+
+    def _run(self, mesh, mode, n):
+        out = np.zeros(max(n, 1))
+        x = mesh._vert
+        check(lib().mcu_pairwise(mesh.nv, mesh.dim, x.ctypes.data, self.kind, None, self.cutoff, mode, out.ctypes.data))
+        return out[:n]
+
+    def integrand(self, mesh):
+        return self._run(mesh, MCU_INTEGRAND, mesh.nv)
+
+    def total(self, mesh):
+        return float(self._run(mesh, MCU_TOTAL, 1)[0])
+
+    def gradient(self, mesh):
+        return self._run(mesh, MCU_GRADIENT, mesh.nv * mesh.dim).reshape(mesh.nv, mesh.dim)

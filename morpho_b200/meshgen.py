@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
-    "icosphere", "perturb_radially", "disk", "tet_cube", "polyline_loop",
+    "IcoTopology", "icosphere", "perturb_radially", "radial_factors", "disk", "tet_cube", "polyline_loop",
     "sphere_points", "edges_from_faces", "write_mesh_file",
 ]
 
@@ -36,95 +36,124 @@ _ICO_FACES = np.array([
 ], dtype=np.int64)
 
 
-def icosphere(f: int, sort_ids: bool = True):
-    """Geodesic icosphere of frequency ``f`` on the unit sphere.
+class IcoTopology:
+    """Index arithmetic of the frequency-``f`` geodesic icosphere, usable face by face so that a rank
+    can build only its own element range of a very large sphere (morpho_b200/partition.py).
 
-    ``20 f^2`` triangles, ``10 f^2 + 2`` vertices (BASELINE.json config 2 uses
-    f = 707: 9 996 980 triangles, 4 998 492 vertices).
-
-    Vertex order (the documented "generator order"): the 12 icosahedron corners,
-    then the interior points of the 30 edges (edge list sorted by (lo, hi) corner
-    id, points ordered from the lower corner), then for each of the 20 faces its
-    interior grid points row by row.  Element order: face by face, row by row,
-    alternating up/down triangles along a row.
+    Vertex order (the documented "generator order"): the 12 icosahedron corners, then the interior
+    points of the 30 edges (edge list sorted by (lo, hi) corner id, points ordered from the lower
+    corner), then for each of the 20 faces its interior grid points row by row.  Element order: face by
+    face, row by row, alternating up/down triangles along a row.
     """
-    if f < 1:
-        raise ValueError("frequency must be >= 1")
-    f = int(f)
-    faces = _ICO_FACES
-    # --- edges -------------------------------------------------------------------
-    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
-    e = np.unique(np.sort(e, axis=1), axis=0)          # 30 x 2, sorted by (lo, hi)
-    assert e.shape[0] == 30
-    edge_id = {(int(a), int(b)): k for k, (a, b) in enumerate(e)}
-    n_edge_int = f - 1
-    n_face_int = (f - 1) * (f - 2) // 2
-    base_edge = 12
-    base_face = 12 + 30 * n_edge_int
-    nv = base_face + 20 * n_face_int
-    assert nv == 10 * f * f + 2
 
-    corners = _ICO_VERTS / np.linalg.norm(_ICO_VERTS, axis=1, keepdims=True)
-    vert = np.empty((nv, 3), dtype=np.float64)
-    vert[:12] = corners
-    if n_edge_int > 0:
-        t = np.arange(1, f, dtype=np.float64)[:, None] / f
-        for k, (a, b) in enumerate(e):
-            vert[base_edge + k * n_edge_int: base_edge + (k + 1) * n_edge_int] = \
-                (1.0 - t) * corners[a] + t * corners[b]
+    def __init__(self, f: int):
+        if f < 1:
+            raise ValueError("frequency must be >= 1")
+        self.f = f = int(f)
+        faces = _ICO_FACES
+        e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+        self.edges = np.unique(np.sort(e, axis=1), axis=0)          # 30 x 2, sorted by (lo, hi)
+        assert self.edges.shape[0] == 30
+        self.edge_id = {(int(a), int(b)): k for k, (a, b) in enumerate(self.edges)}
+        self.n_edge_int = f - 1
+        self.n_face_int = (f - 1) * (f - 2) // 2
+        self.base_edge = 12
+        self.base_face = 12 + 30 * self.n_edge_int
+        self.nv = self.base_face + 20 * self.n_face_int
+        self.nel = 20 * f * f
+        self.tri_per_face = f * f
+        self.corners = _ICO_VERTS / np.linalg.norm(_ICO_VERTS, axis=1, keepdims=True)
+        rows = np.arange(f + 1)
+        row_len = np.clip(f - rows - 1, 0, None)
+        row_len[0] = 0
+        self.row_off = np.concatenate([[0], np.cumsum(row_len)])    # row_off[i] = interior points before row i
 
-    # grid coordinates (i, j) with i + j <= f ; point = (k A + i B + j C) / f, k = f-i-j
-    ii, jj = np.meshgrid(np.arange(f + 1), np.arange(f + 1), indexing="ij")
-    valid = (ii + jj) <= f
-    kk = f - ii - jj
-    # row offsets of interior points: row i (1..f-2) holds j = 1..f-i-1
-    rows = np.arange(f + 1)
-    row_len = np.clip(f - rows - 1, 0, None)
-    row_len[0] = 0
-    row_off = np.concatenate([[0], np.cumsum(row_len)])[: f + 1]
-
-    def edge_point(p, q, t):
-        """global id of the point t/f of the way from corner p to corner q (0<t<f)."""
+    def _edge_point(self, p, q, t):
+        """global id of the point t/f of the way from corner p to corner q (0 < t < f)."""
         lo, hi = (p, q) if p < q else (q, p)
-        tt = t if p < q else f - t
-        return base_edge + edge_id[(lo, hi)] * n_edge_int + (tt - 1)
+        tt = t if p < q else self.f - t
+        return self.base_edge + self.edge_id[(lo, hi)] * self.n_edge_int + (tt - 1)
 
-    conn_all = []
-    for fi, (A, B, C) in enumerate(faces):
-        A, B, C = int(A), int(B), int(C)
+    def face_grid(self, fi: int) -> np.ndarray:
+        """(f+1) x (f+1) array G[i, j] of global vertex ids of face ``fi`` (-1 outside i + j <= f);
+        the grid point is (k A + i B + j C) / f with k = f - i - j."""
+        f = self.f
+        A, B, C = (int(x) for x in _ICO_FACES[fi])
+        ii, jj = np.meshgrid(np.arange(f + 1), np.arange(f + 1), indexing="ij")
+        kk = f - ii - jj
         G = np.full((f + 1, f + 1), -1, dtype=np.int64)
-        interior = valid & (ii >= 1) & (jj >= 1) & (kk >= 1)
-        G[interior] = base_face + fi * n_face_int + row_off[ii[interior]] + (jj[interior] - 1)
-        if n_face_int > 0:
-            w = np.stack([kk[interior], ii[interior], jj[interior]], axis=1).astype(np.float64) / f
-            vert[G[interior]] = w[:, 0:1] * corners[A] + w[:, 1:2] * corners[B] + w[:, 2:3] * corners[C]
+        interior = (kk >= 1) & (ii >= 1) & (jj >= 1)
+        G[interior] = self.base_face + fi * self.n_face_int + self.row_off[ii[interior]] + (jj[interior] - 1)
         G[0, 0], G[f, 0], G[0, f] = A, B, C
         if f > 1:
             t = np.arange(1, f)
-            G[t, 0] = edge_point(A, B, t)          # j = 0 : A -> B, parameter i
-            G[0, t] = edge_point(A, C, t)          # i = 0 : A -> C, parameter j
-            G[f - t, t] = edge_point(B, C, t)      # k = 0 : B -> C, parameter j
-        # triangles
+            G[t, 0] = self._edge_point(A, B, t)          # j = 0 : A -> B, parameter i
+            G[0, t] = self._edge_point(A, C, t)          # i = 0 : A -> C, parameter j
+            G[f - t, t] = self._edge_point(B, C, t)      # k = 0 : B -> C, parameter j
+        return G
+
+    def face_triangles(self, fi: int) -> np.ndarray:
+        """f^2 x 3 global vertex ids of the triangles of face ``fi`` in element order (unsorted ids)."""
+        f = self.f
+        G = self.face_grid(fi)
+        ii, jj = np.meshgrid(np.arange(f + 1), np.arange(f + 1), indexing="ij")
         iu, ju = np.nonzero((ii + jj) <= f - 1)
         up = np.stack([G[iu, ju], G[iu + 1, ju], G[iu, ju + 1]], axis=1)
         idn, jdn = np.nonzero((ii + jj) <= f - 2)
         dn = np.stack([G[idn + 1, jdn], G[idn + 1, jdn + 1], G[idn, jdn + 1]], axis=1)
         key = np.concatenate([iu * (2 * f + 2) + 2 * ju, idn * (2 * f + 2) + 2 * jdn + 1])
-        tri = np.concatenate([up, dn])[np.argsort(key, kind="stable")]
-        conn_all.append(tri)
-    conn = np.concatenate(conn_all).astype(np.int32)
+        return np.concatenate([up, dn])[np.argsort(key, kind="stable")]
+
+    def positions(self, ids: np.ndarray) -> np.ndarray:
+        """Unit-sphere positions of the given global vertex ids (any order, any subset)."""
+        f = self.f
+        ids = np.asarray(ids, dtype=np.int64)
+        out = np.empty((ids.shape[0], 3), dtype=np.float64)
+        c = self.corners
+        is_corner = ids < self.base_edge
+        out[is_corner] = c[ids[is_corner]]
+        is_edge = (ids >= self.base_edge) & (ids < self.base_face)
+        if is_edge.any():
+            loc = ids[is_edge] - self.base_edge
+            k, t = loc // self.n_edge_int, (loc % self.n_edge_int + 1).astype(np.float64)[:, None] / f
+            out[is_edge] = (1.0 - t) * c[self.edges[k, 0]] + t * c[self.edges[k, 1]]
+        is_face = ids >= self.base_face
+        if is_face.any():
+            loc = ids[is_face] - self.base_face
+            fi, r = loc // self.n_face_int, loc % self.n_face_int
+            i = np.searchsorted(self.row_off, r, side="right") - 1
+            j = r - self.row_off[i] + 1
+            w = np.stack([f - i - j, i, j], axis=1).astype(np.float64) / f
+            tri = _ICO_FACES[fi]
+            out[is_face] = w[:, 0:1] * c[tri[:, 0]] + w[:, 1:2] * c[tri[:, 1]] + w[:, 2:3] * c[tri[:, 2]]
+        out /= np.linalg.norm(out, axis=1, keepdims=True)
+        return out
+
+
+def icosphere(f: int, sort_ids: bool = True):
+    """Geodesic icosphere of frequency ``f`` on the unit sphere.
+
+    ``20 f^2`` triangles, ``10 f^2 + 2`` vertices (BASELINE.json config 2 uses
+    f = 707: 9 996 980 triangles, 4 998 492 vertices).  Ordering: see :class:`IcoTopology`.
+    """
+    topo = IcoTopology(f)
+    conn = np.concatenate([topo.face_triangles(fi) for fi in range(20)]).astype(np.int32)
     assert conn.shape[0] == 20 * f * f and conn.min() >= 0
-    vert /= np.linalg.norm(vert, axis=1, keepdims=True)
+    vert = topo.positions(np.arange(topo.nv))
     if sort_ids:
         conn.sort(axis=1)
     return np.ascontiguousarray(vert), np.ascontiguousarray(conn)
 
 
+def radial_factors(nv: int, amplitude: float = 0.01, seed: int = 12345) -> np.ndarray:
+    """``1 + amplitude * u_i`` for all ``nv`` vertices of a mesh (shared by the partitioned builder)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return 1.0 + amplitude * rng.uniform(-1.0, 1.0, size=nv)
+
+
 def perturb_radially(vert: np.ndarray, amplitude: float = 0.01, seed: int = 12345) -> np.ndarray:
     """``x -> x (1 + amplitude * u)``, ``u ~ U(-1, 1)``, PCG64(seed)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    u = rng.uniform(-1.0, 1.0, size=vert.shape[0])
-    return np.ascontiguousarray(vert * (1.0 + amplitude * u)[:, None])
+    return np.ascontiguousarray(vert * radial_factors(vert.shape[0], amplitude, seed)[:, None])
 
 
 def disk(n: int, dim: int = 3):

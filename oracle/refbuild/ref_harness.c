@@ -324,5 +324,7 @@ double refh_time(void *func, const char *method, void *mesh, void *sel, void *fi
     return tot / (double) (reps > 0 ? reps : 1);
 }
 
-/* functional_fdstepsize as the reference computes it (functional.c:46-58) */
+/* functional_fdstepsize as the reference computes it (functional.c:46-58); it is a non-static
+ * function of the library but has no prototype in functional.h */
+double functional_fdstepsize(double x, int order);
 double refh_fdstepsize(double x, int order) { return functional_fdstepsize(x, order); }

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU oracle (plain-C restatement).  Built on demand with gcc."""
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "libmorpho_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libmorpho_oracle.so"])
+    from oracle.oracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    """The unmodified reference behind our harness, when oracle/_ref has been built."""
+    from oracle.oracle import Reference, reference_available
+    if not reference_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    try:
+        return Reference(0)
+    except OSError as e:      # e.g. OpenBLAS of the image not found
+        pytest.skip(f"reference harness not loadable: {e}")
+
+
+@pytest.fixture(scope="session")
+def cases():
+    from tests.golden.cases import all_cases
+    return all_cases()
+
+
+def run_backend(backend, case, ev, gold_selorder=None):
+    """Evaluate one case entry on `backend` ('oracle' object or the CUDA package)."""
+    raise NotImplementedError

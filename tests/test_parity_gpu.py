@@ -1,0 +1,218 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes → libmorpho_cuda.so),
+against (a) the committed golden vectors of the unmodified reference, (b) the CPU oracle on the same
+seeded inputs, and (c) size-independent properties at BASELINE.json's full size.
+
+Tolerances are the ones in tests/parity.py: 1e-12 for energies, integrands and analytic gradients;
+2e-9 (of the gradient scale) for the finite-difference family, whose reference values carry
+their own ~1e-10 round-off amplified by 1/(2h)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import FunctionalSpec
+from tests.golden.cases import all_cases, eval_key
+from tests.parity import TOL_EXACT, measure, rel_array, tolerance
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = all_cases()
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import morpho_b200 as mb
+    mb.init(0)
+    return mb
+
+
+def _build(mb, case):
+    g = case["grades"]
+    mesh = mb.Mesh(case["vert"], edges=g.get(1), faces=g.get(2), volumes=g.get(3))
+    fields = {k: mb.Field(mesh, np.asarray(v).reshape(mesh.nv, -1)) for k, v in case["fields"].items()}
+    return mesh, fields
+
+
+def _functional(mb, ev, fields):
+    f = dict(ev["f"])
+    name = f.pop("name")
+    fl = [fields[n] for n in f.pop("fields", [])]
+    return getattr(mb, name)(*fl, **f)
+
+
+def _cuda_eval(mb, mesh, fields, ev):
+    func = _functional(mb, ev, fields)
+    args = [mesh]
+    if "sel" in ev:
+        args.append(mb.Selection(mesh, ids={ev["sel"][0]: ev["sel"][1]}))
+    m = ev["method"]
+    if m == "fieldgradient":
+        return func.fieldgradient(fields[ev["wrt"]], *args)
+    return getattr(func, m)(*args)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cuda_matches_reference_golden(mb, case):
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    mesh, fields = _build(mb, case)
+    worst = {}
+    for i, ev in enumerate(case["evals"]):
+        key = eval_key(i, ev)
+        got = _cuda_eval(mb, mesh, fields, ev)
+        assert got is not None, key
+        err = measure(ev, got, gold[key], case)
+        worst[(ev["f"]["name"], ev["method"])] = max(worst.get((ev["f"]["name"], ev["method"]), 0.0), err)
+        assert err <= tolerance(ev), f"{case['name']}:{key} err {err:.3e} > {tolerance(ev):.1e}"
+    print({k: f"{v:.1e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("f", [1, 7, 40])
+def test_transpose_bit_exact(mb, oracle, f):
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(f)
+    m = mb.Mesh(v, faces=c)
+    tptr, tidx = m.transpose(2)
+    tptr0, tidx0 = oracle.transpose(v.shape[0], c)
+    np.testing.assert_array_equal(tptr, tptr0)
+    np.testing.assert_array_equal(tidx, tidx0)
+
+
+@pytest.mark.parametrize("f", [3, 22, 70, 224])
+def test_sphere_rungs_against_oracle(mb, oracle, f):
+    """SURVEY §8d config 2 rungs: Area / VolumeEnclosed total, integrand, gradient on both assembly paths."""
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(f)
+    v = mg.perturb_radially(v)
+    m = mb.Mesh(v, faces=c)
+    for cls, name in ((mb.Area, "Area"), (mb.VolumeEnclosed, "VolumeEnclosed")):
+        spec = FunctionalSpec(name)
+        fn = cls()
+        t0 = oracle.total(v, {2: c}, spec)
+        assert abs(fn.total(m) - t0) <= TOL_EXACT * abs(t0)
+        assert rel_array(fn.integrand(m), oracle.integrand(v, {2: c}, spec)) <= TOL_EXACT
+        g0 = oracle.gradient(v, {2: c}, spec)
+        res = {}
+        for path in (mb._lib.MCU_PATH_GATHER, mb._lib.MCU_PATH_PATCH):
+            mb.set_option("gradient_path", path)
+            g = fn.gradient(m)
+            assert rel_array(g, g0, rows=3) <= TOL_EXACT, (name, path)
+            g2 = fn.gradient(m)
+            np.testing.assert_array_equal(g, g2)     # deterministic: bitwise reproducible run to run
+            res[path] = g
+        mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+        # the gather path sums in the reference's order with the reference's formulas
+        assert rel_array(res[mb._lib.MCU_PATH_GATHER], g0, rows=3) <= 1e-14
+
+
+def test_vertex_update_invalidates_mirror(mb, oracle):
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(10)
+    m = mb.Mesh(v, faces=c)
+    a = mb.Area()
+    t1 = a.total(m)
+    v2 = mg.perturb_radially(v, 0.1, 5)
+    m.setvertexmatrix(v2)
+    t2 = a.total(m)
+    assert abs(t2 - oracle.total(v2, {2: c}, FunctionalSpec("Area"))) <= TOL_EXACT * t2
+    assert t1 != t2
+
+
+def test_edge_cases(mb, oracle):
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(4)
+    m = mb.Mesh(v, faces=c)
+    # empty selection: totals 0, gradient all zeros, integrand all zeros
+    empty = mb.Selection(m, ids={2: []})
+    assert mb.Area().total(m, empty) == 0.0
+    assert not mb.Area().gradient(m, empty).any()
+    assert not mb.Area().integrand(m, empty).any()
+    # missing grade → FnctlELNtFnd (functional.c:115-129)
+    with pytest.raises(mb.MorphoError) as ei:
+        mb.Length().total(m)
+    assert ei.value.id == "FnctlELNtFnd"
+    with pytest.raises(mb.MorphoError):
+        mb.Volume().total(m)
+    # degenerate triangle → gradient is nil (functional.c:2090, 412-415); integrand still defined
+    vd = v.copy()
+    vd[c[0, 1]] = vd[c[0, 0]]
+    md = mb.Mesh(vd, faces=c)
+    for path in (mb._lib.MCU_PATH_GATHER, mb._lib.MCU_PATH_PATCH):
+        mb.set_option("gradient_path", path)
+        assert mb.Area().gradient(md) is None
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+    assert mb.Area().integrand(md)[0] == 0.0
+    # a vertex at the origin → VolEnclZero (functional.c:2148-2151)
+    vz = v.copy()
+    vz[c[5, 2]] = 0.0
+    mz = mb.Mesh(vz, faces=c)
+    with pytest.raises(mb.MorphoError) as ei:
+        mb.VolumeEnclosed().gradient(mz)
+    assert ei.value.id == "VolEnclZero"
+    # isolated vertices get zero rows; single-element mesh works
+    vi = np.concatenate([v, [[2.0, 2.0, 2.0]]])
+    mi = mb.Mesh(vi, faces=c)
+    for path in (mb._lib.MCU_PATH_GATHER, mb._lib.MCU_PATH_PATCH):
+        mb.set_option("gradient_path", path)
+        g = mb.Area().gradient(mi)
+        assert not g[-1].any()
+        assert rel_array(g[:-1], oracle.gradient(v, {2: c}, FunctionalSpec("Area")), rows=3) <= TOL_EXACT
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+    one = mb.Mesh(np.array([[1, 0, 0], [-0.5, 0.866025, 0], [-0.5, -0.866025, 0]], float), faces=[[0, 1, 2]])
+    assert abs(mb.Area().integrand(one)[0] - 1.29904) < 1e-5    # test/functionals/area/area.morpho:9-10
+
+
+def test_selection_boundary_and_addgrade(mb, oracle):
+    from morpho_b200 import meshgen as mg
+    v, f, b = mg.disk(6, 3)
+    m = mb.Mesh(v, faces=f)
+    edges = m.addgrade(1)
+    np.testing.assert_array_equal(edges, oracle.edges_from(f))           # mesh_addgrade order, bit-exact
+    bnd = mb.Selection(m, boundary=True)
+    ids = bnd.idlistforgrade(1)
+    key = lambda a: a[:, 0].astype(np.int64) * v.shape[0] + a[:, 1]
+    assert sorted(key(edges[ids])) == sorted(key(b))
+    L = mb.Length().total(m, bnd)
+    assert abs(L - oracle.total(v, {1: edges}, FunctionalSpec("Length"), ids)) <= TOL_EXACT * L
+
+
+def test_pairwise_against_oracle(mb, oracle):
+    from morpho_b200 import meshgen as mg
+    x = mg.sphere_points(1500, 12345)
+    m = mb.Mesh(x)
+    p = mb.PairwisePotential("coulomb")
+    e0 = oracle.pairwise_coulomb(x, "integrand")
+    g0 = oracle.pairwise_coulomb(x, "gradient")
+    assert rel_array(p.integrand(m), e0) <= TOL_EXACT
+    assert abs(p.total(m) - e0.sum()) <= TOL_EXACT * e0.sum()
+    assert rel_array(p.gradient(m), g0, rows=3) <= TOL_EXACT
+    pc = mb.PairwisePotential("coulomb", cutoff=0.5)
+    assert rel_array(pc.gradient(m), oracle.pairwise_coulomb(x, "gradient", 0.5), rows=3) <= TOL_EXACT
+
+
+def test_full_size_properties(mb):
+    """BASELINE.json config 2 at full size (icosphere f=707: 9 996 980 triangles): properties that need no
+    oracle.  Area is homogeneous of degree 2 and VolumeEnclosed of degree 3 in the coordinates
+    (Euler: x.grad = k f); both are translation... Area is translation invariant (sum of rows = 0);
+    the two assembly paths agree to 1e-12; the result is bitwise reproducible."""
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(707)
+    v = mg.perturb_radially(v)
+    m = mb.Mesh(v, faces=c)
+    assert c.shape[0] == 9996980 and v.shape[0] == 4998492
+    a, ve = mb.Area(), mb.VolumeEnclosed()
+    A, V = a.total(m), ve.total(m)
+    assert abs(A - a.integrand(m).sum()) <= 1e-12 * A
+    grads = {}
+    for path in (mb._lib.MCU_PATH_GATHER, mb._lib.MCU_PATH_PATCH):
+        mb.set_option("gradient_path", path)
+        ga, gv = a.gradient(m), ve.gradient(m)
+        scale = np.linalg.norm(ga, axis=1).max()
+        assert np.abs(ga.sum(axis=0)).max() <= 1e-9 * scale * np.sqrt(len(ga))
+        assert abs((ga * v).sum() - 2 * A) <= 1e-11 * A
+        assert abs((gv * v).sum() - 3 * V) <= 1e-11 * V
+        grads[path] = (ga, gv)
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+    (ga1, gv1), (ga2, gv2) = grads[mb._lib.MCU_PATH_GATHER], grads[mb._lib.MCU_PATH_PATCH]
+    assert rel_array(ga2, ga1, rows=3) <= TOL_EXACT
+    assert rel_array(gv2, gv1, rows=3) <= TOL_EXACT
+    np.testing.assert_array_equal(a.gradient(m), ga2 if m.count(2) >= 4096 else ga1)
