@@ -211,7 +211,6 @@ def run_ours(args):
     log(f"[rank {rank}] f={f}: {nel_local} of {nel_global} triangles, {vert.shape[0]} vertices, "
         f"{part.n_shared} shared ({time.time() - t0:.1f}s)")
 
-    mb.set_option("patch_kernel", args.patch_kernel)
     if args.patch_owned:
         mb.set_option("patch_max_owned", args.patch_owned)
     mesh = mb.Mesh(vert, faces=conn)
@@ -309,7 +308,7 @@ def run_ours(args):
     value = evals_per_step / (ms_step * 1e-3) / 1e6
     e2e_value = evals_per_step / (ms_e2e * 1e-3) / 1e6
     peak, how = measured_peak()
-    kname = "k_patch_vgather" if args.patch_kernel == 0 else "k_patch_grad"
+    kname = "k_patch_ring"
     ms_dom, dom = (ms_area, kname + "<Area>") if ms_area >= ms_vol else (ms_vol, kname + "<VolumeEnclosed>")
     achieved = BYTES_PER_ELEM_GRADIENT * nel_local / (ms_dom * 1e-3) / 1e9
     traffic = None
@@ -325,9 +324,9 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"icosphere f={f} ({nel_global} triangles global, {nel_local} per GPU), radial perturbation 1%, seed 12345; "
                                "step = Area.gradient + VolumeEnclosed.gradient (2 element-evals per triangle)",
-                   "inputs": "larger than L2 (vertex matrix 120 MB + packed incidence 46 MB + gradient 120 MB per functional)",
+                   "inputs": "larger than L2 (vertex matrix 120 MB + ring tables 101 MB + gradient 120 MB per functional)",
                    "partition": "contiguous element ranges per GPU; shared-vertex rows all-gathered over NCCL" if world > 1 else "single GPU",
-                   "gradient_path": "patch, vertex-centric gather in shared memory (owner computes, reference summation order)" if args.patch_kernel == 0 else "patch, coloured element-centric accumulation in shared memory",
+                   "gradient_path": "persistent patch kernel: bulk-async (TMA) staging of vertex runs into a 3-stage shared-memory ring, one consumer thread per owned vertex walks its ring (owner computes, no atomics)",
                    "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(vert.nbytes), "d2h_bytes_per_step": int(2 * nout * 8),
@@ -354,7 +353,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--freq", type=int, default=707, help="icosphere frequency per GPU (707 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--patch-kernel", type=int, default=0, help="0 = vertex-centric patch kernel (default), 1 = coloured element-centric")
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     args = ap.parse_args()
     if args.impl == "reference":

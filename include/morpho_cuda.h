@@ -161,11 +161,11 @@ int mcu_device_free(void *ptr);
 int mcu_flush_l2(void);                     /* overwrite a > L2-sized scratch buffer */
 
 /* ---- introspection of the patch planner (pure host code, no CUDA call): used by the CPU tests
- *      of the host logic.  counts = {patches, vertex-list entries, packed triangles, colour
- *      offsets, max colours, ints per header, slice offsets, incidence entries}. Output arrays may be NULL. ---- */
-int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, long counts[8],
-                         int *hdr_out, int *vtx_out, unsigned *elems_out, int *elem_ids_out, int *color_out,
-                         int *slice_out, unsigned short *ents_out);
+ *      of the host logic.  counts = {patches, runs, table words, ints per header, max slots, max table
+ *      bytes, halo vertices, alignment slots, modelled shared-load wavefronts, ideal wavefronts}.
+ *      Output arrays may be NULL. ---- */
+int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, long counts[10],
+                         int *hdr_out, int *runs_out, unsigned *tab_out);
 
 #ifdef __cplusplus
 }

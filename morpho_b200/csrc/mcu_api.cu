@@ -139,7 +139,8 @@ mcu_mesh *mcu_mesh_create(int dim, int nv) {
     if ((dim != 2 && dim != 3) || nv < 0) { mcu_set_error("mesh dim must be 2 or 3"); return nullptr; }
     mcu_mesh *m = new mcu_mesh();
     m->dim = dim; m->nv = nv;
-    size_t bytes = sizeof(double) * (size_t) std::max(nv, 1) * dim;
+    // + one spare row pair: the patch kernel copies runs of vertices padded to an even count (mcu_patch.cu)
+    size_t bytes = sizeof(double) * ((size_t) std::max(nv, 1) + 2) * dim;
     if (cudaMalloc((void **) &m->d_vert, bytes) != cudaSuccess ||
         cudaMalloc((void **) &m->d_partials, sizeof(CompSum) * 148 * 8) != cudaSuccess ||
         cudaMalloc((void **) &m->d_scalar, 64) != cudaSuccess ||

@@ -1,51 +1,66 @@
-// mcu_patch.h — data structures of the shared-memory patch decomposition (mcu_patch.cu).
+// mcu_patch.h — data structures of the patch decomposition behind the triangle-mesh gradient kernel
+// (mcu_patch.cu).  See DESIGN.md §3 for the layout and §4 for the kernel.
 #pragma once
 #include <cstdint>
 #include <vector>
 
-#define MCU_PATCH_MAX_LOCAL 1024      // local vertex ids are 10 bit
-#define MCU_PATCH_MAX_COLORS 64
-#define MCU_PATCH_DEFAULT_OWNED 768
+#define MCU_PATCH_MAX_SLOTS 1024      // slot indices are 10 bit
+#define MCU_PATCH_MAX_OWNED 512       // one consumer thread per owned vertex, 16 consumer warps
+#define MCU_PATCH_DEFAULT_OWNED 512
+#define MCU_PATCH_MAX_TAB_BYTES 24576 // staged table of one patch (ring entries + owned ids)
 
-struct McuPatchHeader {
-    int vtx_off;    // offset of this patch's local vertex list (owned first, then halo)
+// One patch = up to 512 "owned" vertices (their gradient rows are produced by this patch's pass) plus the
+// halo: every other vertex that shares a triangle with an owned one.  The local vertices occupy SLOTS of a
+// shared-memory coordinate array.  Slots are laid out as RUNS of consecutive global vertex ids (each run starts
+// at an even id and has even length, so that its 24-byte rows form a 16-byte aligned, 16-byte granular block of
+// the vertex matrix): one bulk-async copy per run moves the coordinates HBM → shared memory.
+struct McuPatchHeader {   // 32 bytes
+    int run_off;    // first run descriptor of this patch in McuPatchPlan::runs
+    int n_runs;
+    int tab_off;    // offset of the staged table in McuPatchPlan::tab, in 16-byte units
+    int tab_bytes;  // multiple of 16
     int n_owned;
-    int n_local;
-    int elem_off;   // offset of the packed triangles, grouped by colour
-    int n_elem;
-    int color_off;  // offset of n_colors+1 relative triangle offsets
-    int n_colors;
-    int slice_off;  // offset of n_slices+1 relative entry offsets (slice = 32 consecutive owned vertices)
-    int n_slices;
-    int ent_off;    // offset of this patch's ring entries (sliced ELL of uint16: [slice][k][lane])
-    int n_ent;      // entries of this patch (multiple of 32)
-    int pad1;
+    int n_slots;    // even, <= MCU_PATCH_MAX_SLOTS
+    int n_slices;   // ceil(n_owned / 32); slice = the 32 owned vertices handled by one warp
+    int tx_bytes;   // bytes the copies of this patch deliver: 24 * n_slots + tab_bytes
 };
 
-#define MCU_PATCH_ENT_NONE 0xffffu    // padding entry of the sliced-ELL ring table
-#define MCU_PATCH_ENT_START 0x8000u  // this ring vertex opens a new strip (no triangle with the previous entry)
+struct McuPatchRun {      // 8 bytes
+    int gid;              // first global vertex id of the run (even)
+    unsigned short slot;  // first slot (even)
+    unsigned short n;     // vertices in the run (even)
+};
+
+// Staged table of a patch (32-bit words):
+//   [0] n_owned [1] n_slices [2] n_ent [3] 0
+//   [4 .. 4+32*n_slices)            global id of the owned vertex of every (slice, lane); -1 = idle lane
+//   [.. + round4(n_slices+1))       entry offset of every slice (relative to the entry array), last = n_ent
+//   n_ent 16-bit entries, sliced ELL: entry k of lane l of slice s at ents[off[s] + 32*k + l]
+// Entries of one owned vertex: [0] its own slot; [1..] the ring of neighbouring vertices as STRIPS: consecutive
+// entries (r_k, r_k+1) form one triangle with the owner unless r_k+1 carries the START bit (it then opens a new
+// strip).  Columns are padded to the slice's length by repeating the last entry with the START bit.
+#define MCU_PATCH_ENT_START 0x8000u
+#define MCU_PATCH_ENT_SLOT 0x03ffu
 
 struct McuPatchPlan {
-    int nv = 0, nel = 0, max_colors = 0;
+    int nv = 0, nel = 0;
     std::vector<McuPatchHeader> hdr;
-    std::vector<int> vtx_ids;
-    std::vector<uint32_t> elems;     // a | b << 10 | c << 20 (local indices of the ascending global ids)
-    std::vector<int> elem_ids;       // global triangle id of each packed slot (tests only)
-    std::vector<int> color_ptr;
-    std::vector<int> slice_ptr;      // per patch n_slices+1 offsets (in entries) relative to ent_off
-    std::vector<uint16_t> ents;      // ring strips: 10-bit local vertex index | START flag (see mcu_patch.cu)
-    int max_local = 0, max_owned = 0, max_ents = 0;
+    std::vector<McuPatchRun> runs;
+    std::vector<uint32_t> tab;       // all staged tables, each 16-byte aligned
+    int max_slots = 0, max_tab_bytes = 0, max_owned = 0, max_runs = 0;
+    long n_halo = 0;                 // halo vertices over all patches (excluding alignment padding)
+    long n_pad = 0;                  // slots that only exist for alignment
+    // shared-memory model of the ring reads (64-bit loads of one half warp hit 16 distinct bank pairs or conflict)
+    long lds_wavefronts = 0, lds_wavefronts_ideal = 0;
 };
 
 struct McuPatchSet {
     McuPatchPlan plan;               // headers + statistics (bulk arrays are dropped after upload)
     int n_patches = 0;
     McuPatchHeader *d_hdr = nullptr;
-    int *d_vtx = nullptr;
-    uint32_t *d_elems = nullptr;
-    int *d_color = nullptr;
-    int *d_slice = nullptr;
-    uint16_t *d_ents = nullptr;
+    McuPatchRun *d_runs = nullptr;
+    uint32_t *d_tab = nullptr;
+    int coords_bytes = 0, stage_bytes = 0, stages = 0, ctas_per_sm = 0;
 };
 
 bool mcu_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, McuPatchPlan &plan);

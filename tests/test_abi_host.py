@@ -60,93 +60,88 @@ def test_binbounds_matches_reference_scheme(L, oracle):
         np.testing.assert_array_equal(b, oracle.binbounds(nel, nb))
 
 
-H_VTX_OFF, H_N_OWNED, H_N_LOCAL, H_ELEM_OFF, H_N_ELEM, H_COLOR_OFF, H_N_COLORS, H_SLICE_OFF, H_N_SLICES, H_ENT_OFF, H_N_ENT = range(11)
-ENT_NONE, ENT_START = 0xFFFF, 0x8000
+H_RUN_OFF, H_N_RUNS, H_TAB_OFF, H_TAB_BYTES, H_N_OWNED, H_N_SLOTS, H_N_SLICES, H_TX_BYTES = range(8)
+ENT_START, ENT_SLOT = 0x8000, 0x03FF
 
 
-def _plan(L, v, c, max_owned=768):
-    counts = (C.c_long * 8)()
-    rc = L.mcu_debug_patch_plan(v.shape[0], c.shape[0], c.ctypes.data, v.ctypes.data, max_owned, counts,
-                                None, None, None, None, None, None, None)
+def _plan(L, v, c, max_owned=512):
+    counts = (C.c_long * 10)()
+    rc = L.mcu_debug_patch_plan(v.shape[0], c.shape[0], c.ctypes.data, v.ctypes.data, max_owned, counts, None, None, None)
     assert rc == 0
-    npatch, nvtx, nel, ncol, maxcol, hints, nslice, nent = list(counts)
+    npatch, nruns, ntab, hints = (int(x) for x in list(counts)[:4])
+    assert hints == 8
     hdr = np.zeros((npatch, hints), dtype=np.int32)
-    vtx = np.zeros(nvtx, dtype=np.int32)
-    el = np.zeros(nel, dtype=np.uint32)
-    eid = np.zeros(nel, dtype=np.int32)
-    col = np.zeros(ncol, dtype=np.int32)
-    sl = np.zeros(nslice, dtype=np.int32)
-    ent = np.zeros(nent, dtype=np.uint16)
+    runs = np.zeros(nruns, dtype=np.dtype([("gid", "<i4"), ("slot", "<u2"), ("n", "<u2")]))
+    tab = np.zeros(ntab, dtype=np.uint32)
     rc = L.mcu_debug_patch_plan(v.shape[0], c.shape[0], c.ctypes.data, v.ctypes.data, max_owned, counts,
-                                hdr.ctypes.data, vtx.ctypes.data, el.ctypes.data, eid.ctypes.data, col.ctypes.data,
-                                sl.ctypes.data, ent.ctypes.data)
+                                hdr.ctypes.data, runs.ctypes.data, tab.ctypes.data)
     assert rc == 0
-    return dict(hdr=hdr, vtx=vtx, el=el, eid=eid, col=col, sl=sl, ent=ent, maxcol=maxcol)
+    return dict(hdr=hdr, runs=runs, tab=tab, counts=[int(x) for x in counts])
 
 
-@pytest.mark.parametrize("f,max_owned", [(3, 768), (12, 768), (30, 200), (30, 768)])
+def _decode_patch(P, h):
+    """slot → global id map (-1 for alignment slots are real ids too: every slot of a run is a vertex row),
+    owned ids per thread, and the entry columns of every owned vertex."""
+    run_off, n_runs, tab_off, tab_bytes, n_owned, n_slots, n_slices, tx = (int(x) for x in h)
+    runs = P["runs"][run_off: run_off + n_runs]
+    slot_gid = np.full(n_slots, -1, dtype=np.int64)
+    at = 0
+    for r in runs:
+        assert r["gid"] % 2 == 0 and r["n"] % 2 == 0 and r["n"] > 0 and r["slot"] == at   # 16-byte aligned bulk copies
+        slot_gid[at: at + r["n"]] = np.arange(r["gid"], r["gid"] + r["n"])
+        at += int(r["n"])
+    assert at == n_slots and n_slots <= 1024
+    assert tab_bytes % 16 == 0 and tx == 24 * n_slots + tab_bytes
+    tab = P["tab"][4 * tab_off: 4 * tab_off + tab_bytes // 4]
+    assert int(tab[0]) == n_owned and int(tab[1]) == n_slices and n_slices == (n_owned + 31) // 32
+    gids = tab[4: 4 + 32 * n_slices].view(np.int32)
+    noff = (n_slices + 4) & ~3
+    offs = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
+    ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(tab[2])]
+    assert offs[0] == 0 and offs[-1] == int(tab[2]) and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 64)
+    return slot_gid, gids, offs, ents
+
+
+@pytest.mark.parametrize("f,max_owned", [(3, 512), (12, 512), (30, 200), (30, 512)])
 def test_patch_plan_is_a_valid_owner_computes_decomposition(L, oracle, f, max_owned):
     from morpho_b200 import meshgen as mg
     v, c = mg.icosphere(f)
     v = mg.perturb_radially(v)
     P = _plan(L, v, c, max_owned)
-    hdr, vtx, el, eid, col = P["hdr"], P["vtx"], P["el"], P["eid"], P["col"]
-    nv, nel = v.shape[0], c.shape[0]
+    nv = v.shape[0]
     tptr, tidx = oracle.transpose(nv, c)
     owned_count = np.zeros(nv, dtype=np.int64)
-    # every vertex→element incidence must be accumulated exactly once, by the owner of the vertex
-    inc_seen = np.zeros((nel, 3), dtype=np.int64)
-    for h in hdr:
-        vtx_off, n_owned, n_local, elem_off, n_elem, color_off, n_colors = (int(x) for x in h[:7])
-        assert 0 < n_owned <= max_owned and n_owned <= n_local <= 1024 and n_colors <= 64
-        loc = vtx[vtx_off: vtx_off + n_local]
-        assert len(np.unique(loc)) == n_local
-        assert np.all(np.diff(loc[:n_owned]) > 0) and np.all(np.diff(loc[n_owned:]) > 0)   # sorted runs → coalesced staging
-        owned_count[loc[:n_owned]] += 1
-        # --- element-centric (coloured) view
-        cp = col[color_off: color_off + n_colors + 1]
-        assert cp[0] == 0 and cp[-1] == n_elem and np.all(np.diff(cp) > 0)
-        packed = el[elem_off: elem_off + n_elem]
-        idx = np.stack([packed & 1023, (packed >> 10) & 1023, packed >> 20], axis=1).astype(np.int64)
-        assert idx.max() < n_local
-        ge = eid[elem_off: elem_off + n_elem]
-        np.testing.assert_array_equal(loc[idx], c[ge])            # local indices decode to the element's ids, in order
-        assert len(np.unique(ge)) == n_elem
-        for k in range(n_colors):                                  # no two triangles of a colour share a vertex
-            used = idx[cp[k]: cp[k + 1]].ravel()
-            assert len(np.unique(used)) == used.size
-        own_mask = idx < n_owned
-        assert np.all(own_mask.any(axis=1))                        # every listed triangle touches an owned vertex
-        r, k = np.nonzero(own_mask)
-        inc_seen[ge[r], k] += 1
-        # --- vertex-centric view: sliced ELL of 16-bit ring STRIPS.  Column i lists ring vertices; consecutive
-        #     entries (without the START bit on the second) span one triangle with the owner.  The multiset of
-        #     triangles decoded must be exactly the owner's incident elements.
-        slice_off, n_slices, ent_off = int(h[H_SLICE_OFF]), int(h[H_N_SLICES]), int(h[H_ENT_OFF])
-        assert n_slices == (n_owned + 31) // 32 and ent_off % 32 == 0 and vtx_off % 4 == 0 and slice_off % 4 == 0
-        sp = P["sl"][slice_off: slice_off + n_slices + 1]
-        assert sp[0] == 0 and np.all(np.diff(sp) % 32 == 0) and sp[-1] == int(h[H_N_ENT])
-        for i in range(n_owned):
-            u = int(loc[i])
+    for h in P["hdr"]:
+        n_owned, n_slices = int(h[H_N_OWNED]), int(h[H_N_SLICES])
+        assert 0 < n_owned <= max_owned
+        slot_gid, gids, offs, ents = _decode_patch(P, h)
+        assert np.all(gids[n_owned:] == -1) and np.all(gids[:n_owned] >= 0)
+        assert np.all(np.diff(gids[:n_owned]) > 0)          # threads in ascending id order → coalesced row writes
+        owned_count[gids[:n_owned]] += 1
+        # vertex-centric view: sliced ELL of 16-bit STRIPS.  Entry 0 is the owner's slot, then ring vertices;
+        # consecutive ring entries (without the START bit on the second) span one triangle with the owner.  The
+        # multiset of triangles decoded must be exactly the owner's incident elements.
+        for i in range(32 * n_slices):
             s, lane = divmod(i, 32)
-            column = P["ent"][ent_off + sp[s] + lane: ent_off + sp[s + 1]: 32].astype(np.int64)
-            valid = column != ENT_NONE
-            nvalid = int(valid.sum())
-            assert np.all(valid[:nvalid]) and not valid[nvalid:].any()       # padding only at the end
+            column = ents[offs[s] + lane: offs[s + 1]: 32].astype(np.int64)
+            assert np.all((column & ENT_SLOT) < int(h[H_N_SLOTS]))
+            if i >= n_owned:
+                assert np.all(column[1:] & ENT_START)       # idle lanes contribute nothing
+                continue
+            u = int(gids[i])
+            assert slot_gid[column[0]] == u and not (column[0] & ENT_START)
             got = []
-            for k2 in range(1, nvalid):
+            for k2 in range(2, len(column)):
                 if column[k2] & ENT_START:
                     continue
-                a, b2 = int(loc[column[k2 - 1] & 1023]), int(loc[column[k2] & 1023])
+                a, b2 = int(slot_gid[column[k2 - 1] & ENT_SLOT]), int(slot_gid[column[k2] & ENT_SLOT])
                 got.append(tuple(sorted((u, a, b2))))
-            assert nvalid == 0 or (column[0] & ENT_START)
             want = [tuple(int(x) for x in c[e]) for e in tidx[tptr[u]: tptr[u + 1]]]
             assert sorted(got) == sorted(want)
-            if len(want) == 6 or len(want) == 5:
-                assert nvalid == len(want) + 1                              # a closed fan is one strip
+            if len(want) in (5, 6):
+                assert int(np.sum((column[2:] & ENT_START) == 0)) == len(want)   # a closed fan is one strip
     assert np.all(owned_count == 1)
-    assert np.all(inc_seen == 1)
-    assert P["maxcol"] <= 64
+    assert P["counts"][9] > 0 and P["counts"][8] >= P["counts"][9]
 
 
 def test_patch_plan_handles_isolated_vertices(L):
@@ -154,5 +149,8 @@ def test_patch_plan_handles_isolated_vertices(L):
     v, c = mg.icosphere(6)
     v = np.concatenate([v, [[3.0, 3.0, 3.0], [-2.0, 0.1, 0.4]]])   # two vertices without elements
     P = _plan(L, np.ascontiguousarray(v), c)
-    owned = np.concatenate([P["vtx"][h[0]: h[0] + h[1]] for h in P["hdr"]])
+    owned = []
+    for h in P["hdr"]:
+        slot_gid, gids, offs, ents = _decode_patch(P, h)
+        owned.extend(int(g) for g in gids if g >= 0)
     assert sorted(owned) == list(range(v.shape[0]))

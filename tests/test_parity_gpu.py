@@ -92,18 +92,16 @@ def test_sphere_rungs_against_oracle(mb, oracle, f):
         assert rel_array(fn.integrand(m), oracle.integrand(v, {2: c}, spec)) <= TOL_EXACT
         g0 = oracle.gradient(v, {2: c}, spec)
         res = {}
-        for path, kern in ((mb._lib.MCU_PATH_GATHER, 0), (mb._lib.MCU_PATH_PATCH, 0), (mb._lib.MCU_PATH_PATCH, 1)):
+        for path in (mb._lib.MCU_PATH_GATHER, mb._lib.MCU_PATH_PATCH):
             mb.set_option("gradient_path", path)
-            mb.set_option("patch_kernel", kern)       # 0 vertex-centric patch kernel, 1 coloured element-centric
             g = fn.gradient(m)
-            assert rel_array(g, g0, rows=3) <= TOL_EXACT, (name, path, kern)
+            assert rel_array(g, g0, rows=3) <= TOL_EXACT, (name, path)
             g2 = fn.gradient(m)
             np.testing.assert_array_equal(g, g2)     # deterministic: bitwise reproducible run to run
-            res[(path, kern)] = g
+            res[path] = g
         mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
-        mb.set_option("patch_kernel", 0)
         # the assembly paths agree with each other as well as with the oracle
-        assert rel_array(res[(mb._lib.MCU_PATH_PATCH, 0)], res[(mb._lib.MCU_PATH_GATHER, 0)], rows=3) <= TOL_EXACT
+        assert rel_array(res[mb._lib.MCU_PATH_PATCH], res[mb._lib.MCU_PATH_GATHER], rows=3) <= TOL_EXACT
 
 
 def test_vertex_update_invalidates_mirror(mb, oracle):
