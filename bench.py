@@ -213,6 +213,9 @@ def run_ours(args):
 
     if args.patch_owned:
         mb.set_option("patch_max_owned", args.patch_owned)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        mb.set_option(k_, int(v_))
     mesh = mb.Mesh(vert, faces=conn)
     area, vol = mb.Area()._desc(), mb.VolumeEnclosed()._desc()
     import ctypes as C
@@ -280,8 +283,8 @@ def run_ours(args):
         _lib.check(L.mcu_eval(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, ha.data_ptr()))
         _lib.check(L.mcu_eval(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, hg.data_ptr()))
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = 1 if args.quick else max(3, min(args.steps, 10))
+    for _ in range(0 if args.quick else 2):
         step_e2e()
     barrier()
     e2s, e2e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,6 +357,8 @@ def main():
     ap.add_argument("--freq", type=int, default=707, help="icosphere frequency per GPU (707 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
+    ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 10:

@@ -98,7 +98,7 @@ def _decode_patch(P, h):
     noff = (n_slices + 4) & ~3
     offs = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
     ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(tab[2])]
-    assert offs[0] == 0 and offs[-1] == int(tab[2]) and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 64)
+    assert offs[0] == 0 and offs[-1] == int(tab[2]) and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 128)
     return slot_gid, gids, offs, ents
 
 
