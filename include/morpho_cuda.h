@@ -167,6 +167,10 @@ int mcu_flush_l2(void);                     /* overwrite a > L2-sized scratch bu
 int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, long counts[10],
                          int *hdr_out, int *runs_out, unsigned *tab_out);
 
+/* timeline diagnostics of the patch kernel (measurement aid): dev_buf receives, per consumer warp of every CTA,
+ * {cycles waiting for data, cycles alive}; NULL disarms. */
+int mcu_debug_patch_profile(long long *dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

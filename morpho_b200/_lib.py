@@ -91,6 +91,7 @@ def lib():
         "mcu_device_malloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "mcu_device_free": (C.c_int, [vp]),
         "mcu_flush_l2": (C.c_int, []),
+        "mcu_debug_patch_profile": (C.c_int, [vp]),
         "mcu_debug_patch_plan": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_long), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -60,6 +60,7 @@ struct McuPatchSet {
     McuPatchHeader *d_hdr = nullptr;
     McuPatchRun *d_runs = nullptr;
     uint32_t *d_tab = nullptr;
+    int *d_sched = nullptr;          // [0] next patch to hand out, [1] CTAs that ran out of work (self re-arming)
     int coords_bytes = 0, stage_bytes = 0, stages = 0, ctas_per_sm = 0;
 };
 
