@@ -31,6 +31,13 @@ struct McuPatchRun {      // 8 bytes
     unsigned short n;     // vertices in the run (even)
 };
 
+// What the producer warps read per patch, addressed by the patch index alone (one latency, prefetchable):
+#define MCU_PATCH_DESC_RUNS 64
+struct McuPatchDesc {     // 544 bytes
+    McuPatchHeader h;
+    McuPatchRun runs[MCU_PATCH_DESC_RUNS];   // the first runs of the patch; the rest (rare) at runs[h.run_off + 64 ..]
+};
+
 // Staged table of a patch (32-bit words):
 //   [0] n_owned [1] n_slices [2] n_ent [3] 0
 //   [4 .. 4+32*n_slices)            global id of the owned vertex of every (slice, lane); -1 = idle lane
@@ -57,7 +64,7 @@ struct McuPatchPlan {
 struct McuPatchSet {
     McuPatchPlan plan;               // headers + statistics (bulk arrays are dropped after upload)
     int n_patches = 0;
-    McuPatchHeader *d_hdr = nullptr;
+    McuPatchDesc *d_desc = nullptr;
     McuPatchRun *d_runs = nullptr;
     uint32_t *d_tab = nullptr;
     int *d_sched = nullptr;          // [0] next patch to hand out, [1] CTAs that ran out of work (self re-arming)
