@@ -1,0 +1,377 @@
+/* morphocuda.c — Morpho EXTENSION that puts libmorpho_cuda.so behind the unchanged builtin API.
+ *
+ * `import morphocuda` (extensions.c:134-154 dlopens <pkgroot>/lib/morphocuda.so and calls
+ * morphocuda_initialize) re-points the C function pointers of the functional classes' `total`,
+ * `integrand` and `gradient` builtins (objectbuiltinfunction.function, builtin.h:60-67; the class method
+ * dictionaries of clss.h:19-28) at the veneers below.  Scripts, the VM, the compiler and optimize.morpho are
+ * untouched: `Area().gradient(mesh)` now evaluates on the GPU and still returns a Matrix bound to the VM.
+ *
+ * The veneers mirror the FUNCTIONAL_* macros of functional.h:276-406: functional_validateargs, then the map,
+ * then morpho_bindobjects.  Behind them a device MIRROR of every Mesh that was evaluated is kept
+ * (mcu_mesh: vertex matrix + incidence of the grades used) and re-uploaded only when stale:
+ *   - vertex data: the Matrix mutators (assign, setindex x3, setcolumn x2, acc, reshape — matrix.c:1590-1632) and
+ *     Mesh.setvertexposition are wrapped "call the original, then mark mirrors of that matrix dirty";
+ *     Mesh.setvertexmatrix swaps the pointer mesh->vert (mesh.c:1145-1160) — caught by comparing pointers
+ *     at every evaluation;
+ *   - connectivity: compared by Sparse object, rix pointer and element count at every evaluation; the in-place
+ *     writers Sparse.setrowindices / setindex and Mesh.addgrade / removegrade / resetconnectivity invalidate;
+ *   - freeing a Mesh (GC) drops its mirror (objecttypedefn.freefn wrapper, object.h:88-96).
+ * MORPHO_CUDA_PARANOID=1 re-uploads the vertex matrix on every call instead of trusting the hooks.
+ *
+ * Anything the CUDA library does not accelerate (fields, symmetries, ragged connectivity, MCU_ERR_UNSUPPORTED)
+ * is passed to the saved reference builtin — that is the reference's own code, not a fallback of ours.
+ *
+ * Built only where the reference headers are available (morpho_b200/ext/build_ext.sh); see INTEGRATION.md.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "morpho.h"
+#include "builtin.h"
+#include "classes.h"
+#include "matrix.h"
+#include "sparse.h"
+#include "mesh.h"
+#include "selection.h"
+#include "field.h"
+#include "functional.h"
+
+#include "morpho_cuda.h"
+
+#define MC_MAXMIRRORS 64
+#define MC_MAXWRAPS 48
+
+typedef struct {
+    objectmesh *mesh;
+    mcu_mesh *m;
+    objectmatrix *vert;      /* mesh->vert when last mirrored */
+    double *elements;        /* vert->elements when last mirrored */
+    int nv, dim;
+    bool vert_dirty;
+    struct { objectsparse *s; int *rix; int nel; bool ok; } conn[4];
+} mc_mirror;
+
+static mc_mirror mirrors[MC_MAXMIRRORS];
+static int nmirrors = 0;
+static bool mc_ready = false, mc_paranoid = false, mc_verbose = false;
+static long mc_stat_evals = 0, mc_stat_vert_uploads = 0, mc_stat_conn_uploads = 0, mc_stat_fallbacks = 0;
+
+static void mc_log(const char *what, const char *detail) {
+    if (mc_verbose) fprintf(stderr, "[morphocuda] %s %s\n", what, detail ? detail : "");
+}
+
+/* ------------------------------------------------------------------ mirrors */
+
+static void mirror_drop(int i) {
+    if (mirrors[i].m) mcu_mesh_destroy(mirrors[i].m);
+    mirrors[i] = mirrors[nmirrors - 1];
+    nmirrors--;
+}
+
+static mc_mirror *mirror_find(objectmesh *mesh) {
+    for (int i = 0; i < nmirrors; i++) if (mirrors[i].mesh == mesh) return &mirrors[i];
+    return NULL;
+}
+
+static void mirror_mark_matrix(objectmatrix *a) {
+    for (int i = 0; i < nmirrors; i++)
+        if (mirrors[i].vert == a || mirrors[i].elements == a->elements) mirrors[i].vert_dirty = true;
+}
+
+static void mirror_invalidate_connectivity(objectmesh *mesh) {
+    for (int i = 0; i < nmirrors; i++)
+        if (!mesh || mirrors[i].mesh == mesh) for (int g = 0; g < 4; g++) mirrors[i].conn[g].ok = false;
+}
+
+/* Mirror of `mesh`, coherent for grade g (0 = vertices only).  NULL → caller uses the reference builtin. */
+static mc_mirror *mirror_get(objectmesh *mesh, grade g) {
+    if (!mesh->vert || mesh->vert->nvals != 1) return NULL;
+    int dim = mesh->vert->nrows, nv = mesh->vert->ncols;
+    if (dim != (int) mesh->dim || (dim != 2 && dim != 3)) return NULL;
+    mc_mirror *mr = mirror_find(mesh);
+    if (mr && (mr->nv != nv || mr->dim != dim)) { mirror_drop((int) (mr - mirrors)); mr = NULL; }
+    if (!mr) {
+        if (nmirrors == MC_MAXMIRRORS) mirror_drop(0);
+        mr = &mirrors[nmirrors];
+        memset(mr, 0, sizeof(*mr));
+        mr->m = mcu_mesh_create(dim, nv);
+        if (!mr->m) return NULL;
+        mr->mesh = mesh; mr->nv = nv; mr->dim = dim; mr->vert_dirty = true;
+        nmirrors++;
+    }
+    if (mr->vert != mesh->vert || mr->elements != mesh->vert->elements) {   /* Mesh.setvertexmatrix swapped the matrix */
+        mr->vert = mesh->vert; mr->elements = mesh->vert->elements; mr->vert_dirty = true;
+    }
+    if (mr->vert_dirty || mc_paranoid) {
+        if (mcu_mesh_set_vertices(mr->m, mesh->vert->elements) != MCU_OK) return NULL;
+        mr->vert_dirty = false;
+        mc_stat_vert_uploads++;
+    }
+    if (g > 0) {
+        objectsparse *s = mesh_getconnectivityelement(mesh, 0, g);
+        if (!s) return mr;                                   /* caller raises FnctlELNtFnd */
+        if (!sparse_checkformat(s, SPARSE_CCS, true, false)) return NULL;
+        int nel = s->ccs.ncols;
+        if (!mr->conn[g].ok || mr->conn[g].s != s || mr->conn[g].rix != s->ccs.rix || mr->conn[g].nel != nel) {
+            /* the device mirror stores rix with an implicit cptr[e] = e (g+1): check the simplicial layout */
+            if (s->ccs.nentries != nel * (g + 1)) return NULL;
+            for (int e = 0; e <= nel; e++) if (s->ccs.cptr[e] != e * (g + 1)) return NULL;
+            for (int k = 0; k < s->ccs.nentries; k++) if (s->ccs.rix[k] < 0 || s->ccs.rix[k] >= nv) return NULL;
+            if (mcu_mesh_set_connectivity(mr->m, g, nel, s->ccs.rix) != MCU_OK) return NULL;
+            mr->conn[g].s = s; mr->conn[g].rix = s->ccs.rix; mr->conn[g].nel = nel; mr->conn[g].ok = true;
+            mc_stat_conn_uploads++;
+        }
+    }
+    return mr;
+}
+
+/* ------------------------------------------------------------------ the veneers */
+
+/* ids of a Selection for grade g: the integer keys of sel->selected[g] (functional.c:226-229) */
+static int selection_ids(objectselection *sel, grade g, int **out) {
+    *out = NULL;
+    if ((unsigned) g >= sel->ngrades) return 0;
+    dictionary *d = &sel->selected[g];
+    int n = 0;
+    int *ids = malloc(sizeof(int) * (d->count > 0 ? d->count : 1));
+    if (!ids) return -1;
+    if (d->count > 0) for (unsigned int k = 0; k < d->capacity; k++)
+        if (MORPHO_ISINTEGER(d->contents[k].key)) ids[n++] = MORPHO_GETINTEGERVALUE(d->contents[k].key);
+    *out = ids;
+    return n;
+}
+
+static bool mesh_has_symmetries(objectmesh *mesh, grade g) {
+    return mesh_getconnectivityelement(mesh, 0, 0) || (g > 0 && mesh_getconnectivityelement(mesh, g, g));
+}
+
+/* One evaluation; returns true when handled (out/err set), false → call the reference builtin */
+static bool mc_eval(vm *v, int nargs, value *args, int functional, grade g, int mode, value *out) {
+    functional_mapinfo info;
+    *out = MORPHO_NIL;
+    if (!mc_ready) return false;
+    if (!functional_validateargs(v, nargs, args, &info)) return true;    /* FnctlIntMsh raised, result nil */
+    if (info.field || mesh_has_symmetries(info.mesh, g)) return false;
+    if (info.sel && info.sel->mode != SELECT_SOME) return false;
+    mc_mirror *mr = mirror_get(info.mesh, g);
+    if (!mr) return false;
+    if (g > 0 && !mesh_getconnectivityelement(info.mesh, 0, g)) {
+        morpho_runtimeerror(v, FUNC_ELNTFND, g);
+        return true;
+    }
+    mcu_functional f;
+    memset(&f, 0, sizeof(f));
+    f.functional = functional; f.grade = g;
+    mcu_selection *sel = NULL;
+    if (info.sel) {
+        int *ids, n = selection_ids(info.sel, g, &ids);
+        if (n < 0) return false;
+        sel = mcu_selection_create(mr->m, g, n, ids);
+        free(ids);
+        if (!sel) return false;
+    }
+    int rc = MCU_OK;
+    objectmatrix *new = NULL;
+    double total = 0.0;
+    switch (mode) {
+        case MCU_TOTAL:
+            rc = mcu_eval(mr->m, &f, sel, MCU_TOTAL, &total);
+            break;
+        case MCU_INTEGRAND: {
+            long n = mcu_result_size(mr->m, &f, MCU_INTEGRAND);
+            new = matrix_new(1, (MatrixIdx_t) n, false);
+            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
+            if (n > 0) rc = mcu_eval(mr->m, &f, sel, MCU_INTEGRAND, new->elements);
+            break;
+        }
+        case MCU_GRADIENT:
+            new = matrix_new(mr->dim, mr->nv, false);
+            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
+            rc = mcu_eval(mr->m, &f, sel, MCU_GRADIENT, new->elements);
+            break;
+        default:
+            rc = MCU_ERR_UNSUPPORTED;
+    }
+    if (sel) mcu_selection_destroy(sel);
+    mc_stat_evals++;
+    if (rc == MCU_OK) {
+        if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
+        else { *out = MORPHO_OBJECT(new); morpho_bindobjects(v, 1, out); }
+        return true;
+    }
+    if (new) object_free((object *) new);
+    if (rc == -1) return true;                                /* allocation error already raised */
+    if (rc == MCU_ERR_DEGENERATE) return true;                /* reference: map aborted, method result nil (functional.c:392,412-415) */
+    if (rc == MCU_ERR_VOLENCLZERO) { morpho_runtimeerror(v, VOLUMEENCLOSED_ZERO); return true; }
+    if (rc == MCU_ERR_ELNOTFOUND) { morpho_runtimeerror(v, FUNC_ELNTFND, g); return true; }
+    mc_stat_evals--;
+    mc_log("not accelerated:", mcu_last_error());
+    return false;
+}
+
+#define MC_VENEER(cls, FID, GRADE, meth, MODE) \
+    static builtinfunction orig_##cls##_##meth = NULL; \
+    static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
+        value out; \
+        if (mc_eval(v, nargs, args, FID, GRADE, MODE, &out)) return out; \
+        mc_stat_fallbacks++; \
+        return orig_##cls##_##meth(v, nargs, args); \
+    }
+#define MC_FUNCTIONAL(cls, FID, GRADE) \
+    MC_VENEER(cls, FID, GRADE, total, MCU_TOTAL) \
+    MC_VENEER(cls, FID, GRADE, integrand, MCU_INTEGRAND) \
+    MC_VENEER(cls, FID, GRADE, gradient, MCU_GRADIENT)
+
+MC_FUNCTIONAL(Length, MCU_F_LENGTH, MESH_GRADE_LINE)
+MC_FUNCTIONAL(Area, MCU_F_AREA, MESH_GRADE_AREA)
+MC_FUNCTIONAL(VolumeEnclosed, MCU_F_VOLUMEENCLOSED, MESH_GRADE_AREA)
+MC_FUNCTIONAL(Volume, MCU_F_VOLUME, MESH_GRADE_VOLUME)
+MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, total, MCU_TOTAL)
+MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, integrand, MCU_INTEGRAND)
+
+/* ------------------------------------------------------------------ write hooks */
+
+typedef enum { WRAP_MATRIX_SELF, WRAP_MESH_VERTS, WRAP_MESH_CONN, WRAP_CONN_ALL } mc_wrapkind;
+static struct { builtinfunction orig; mc_wrapkind kind; } wraps[MC_MAXWRAPS];
+static int nwraps = 0;
+
+static value wrap_call(int slot, vm *v, int nargs, value *args) {
+    value self = MORPHO_SELF(args);
+    /* resolve the target BEFORE the call (the method may free or replace things), mark AFTER it */
+    objectmatrix *mat = (wraps[slot].kind == WRAP_MATRIX_SELF && MORPHO_ISMATRIX(self)) ? MORPHO_GETMATRIX(self) : NULL;
+    objectmesh *mesh = ((wraps[slot].kind == WRAP_MESH_VERTS || wraps[slot].kind == WRAP_MESH_CONN) && MORPHO_ISMESH(self)) ? MORPHO_GETMESH(self) : NULL;
+    value r = wraps[slot].orig(v, nargs, args);
+    switch (wraps[slot].kind) {
+        case WRAP_MATRIX_SELF: if (mat) mirror_mark_matrix(mat); break;
+        case WRAP_MESH_VERTS: { mc_mirror *mr = mesh ? mirror_find(mesh) : NULL; if (mr) mr->vert_dirty = true; break; }
+        case WRAP_MESH_CONN: mirror_invalidate_connectivity(mesh); break;
+        case WRAP_CONN_ALL: mirror_invalidate_connectivity(NULL); break;
+    }
+    return r;
+}
+/* C has no closures: a pool of numbered trampolines, one per wrapped builtin */
+#define TR(n) static value tr_##n(vm *v, int nargs, value *args) { return wrap_call(n, v, nargs, args); }
+TR(0) TR(1) TR(2) TR(3) TR(4) TR(5) TR(6) TR(7) TR(8) TR(9) TR(10) TR(11) TR(12) TR(13) TR(14) TR(15)
+TR(16) TR(17) TR(18) TR(19) TR(20) TR(21) TR(22) TR(23) TR(24) TR(25) TR(26) TR(27) TR(28) TR(29) TR(30) TR(31)
+TR(32) TR(33) TR(34) TR(35) TR(36) TR(37) TR(38) TR(39) TR(40) TR(41) TR(42) TR(43) TR(44) TR(45) TR(46) TR(47)
+#define TRN(n) tr_##n
+static builtinfunction trampolines[MC_MAXWRAPS] = {
+    TRN(0), TRN(1), TRN(2), TRN(3), TRN(4), TRN(5), TRN(6), TRN(7), TRN(8), TRN(9), TRN(10), TRN(11), TRN(12), TRN(13), TRN(14), TRN(15),
+    TRN(16), TRN(17), TRN(18), TRN(19), TRN(20), TRN(21), TRN(22), TRN(23), TRN(24), TRN(25), TRN(26), TRN(27), TRN(28), TRN(29), TRN(30), TRN(31),
+    TRN(32), TRN(33), TRN(34), TRN(35), TRN(36), TRN(37), TRN(38), TRN(39), TRN(40), TRN(41), TRN(42), TRN(43), TRN(44), TRN(45), TRN(46), TRN(47)};
+
+/* every builtin implementation behind class.method (a plain builtin or the members of a metafunction) */
+static int method_impls(const char *cls, const char *method, objectbuiltinfunction **out, int cap) {
+    value klass = builtin_findclassfromcstring((char *) cls);
+    if (!MORPHO_ISCLASS(klass)) return 0;
+    objectstring key = MORPHO_STATICSTRING((char *) method);
+    value m;
+    if (!dictionary_get(&MORPHO_GETCLASS(klass)->methods, MORPHO_OBJECT(&key), &m)) return 0;
+    int n = 0;
+    if (MORPHO_ISBUILTINFUNCTION(m)) {
+        if (n < cap) out[n++] = MORPHO_GETBUILTINFUNCTION(m);
+    } else if (MORPHO_ISMETAFUNCTION(m)) {
+        objectmetafunction *mf = MORPHO_GETMETAFUNCTION(m);
+        for (unsigned int i = 0; i < mf->fns.count; i++)
+            if (MORPHO_ISBUILTINFUNCTION(mf->fns.data[i]) && n < cap) out[n++] = MORPHO_GETBUILTINFUNCTION(mf->fns.data[i]);
+    }
+    return n;
+}
+
+static int hook_writers(const char *cls, const char *method, mc_wrapkind kind) {
+    objectbuiltinfunction *impl[16];
+    int n = method_impls(cls, method, impl, 16), done = 0;
+    for (int i = 0; i < n; i++) {
+        bool ours = false;
+        for (int k = 0; k < MC_MAXWRAPS; k++) if (impl[i]->function == trampolines[k]) ours = true;
+        if (ours) continue;                                   /* the same builtin registered under two names */
+        if (nwraps == MC_MAXWRAPS) { fprintf(stderr, "[morphocuda] out of trampolines for %s.%s\n", cls, method); break; }
+        wraps[nwraps].orig = impl[i]->function; wraps[nwraps].kind = kind;
+        impl[i]->function = trampolines[nwraps++];
+        done++;
+    }
+    return done;
+}
+
+static int patch_method(const char *cls, const char *method, builtinfunction ours, builtinfunction *orig) {
+    objectbuiltinfunction *impl[4];
+    int n = method_impls(cls, method, impl, 4);
+    if (n != 1) { fprintf(stderr, "[morphocuda] %s.%s not found as a single builtin; left alone\n", cls, method); return 0; }
+    if (impl[0]->function == ours) return 1;
+    *orig = impl[0]->function;
+    impl[0]->function = ours;
+    return 1;
+}
+
+/* Mesh objects that die take their mirror with them */
+static objectfreefn orig_meshfree = NULL;
+static void mc_meshfree(object *obj) {
+    mc_mirror *mr = mirror_find((objectmesh *) obj);
+    if (mr) mirror_drop((int) (mr - mirrors));
+    if (orig_meshfree) orig_meshfree(obj);
+}
+
+/* ------------------------------------------------------------------ script-visible helpers */
+
+/* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference] */
+static value mc_stats(vm *v, int nargs, value *args) {
+    value vals[4] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
+                     MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks)};
+    objectlist *l = object_newlist(4, vals);
+    if (!l) return MORPHO_NIL;
+    return morpho_wrapandbind(v, (object *) l);
+}
+
+/* ------------------------------------------------------------------ extension entry points */
+
+#define PATCH(cls, meth) npatched += patch_method(#cls, #meth, mc_##cls##_##meth, &orig_##cls##_##meth)
+
+void morphocuda_initialize(void) {
+    const char *dev = getenv("MORPHO_CUDA_DEVICE");
+    mc_paranoid = getenv("MORPHO_CUDA_PARANOID") && atoi(getenv("MORPHO_CUDA_PARANOID")) != 0;
+    mc_verbose = getenv("MORPHO_CUDA_VERBOSE") && atoi(getenv("MORPHO_CUDA_VERBOSE")) != 0;
+    builtin_addfunction("cudastats", mc_stats, MORPHO_FN_ALLOCATES);
+    if (mcu_init(dev ? atoi(dev) : 0) != MCU_OK) {
+        /* no CPU path of ours exists: without a usable GPU nothing is patched and the reference runs as shipped */
+        fprintf(stderr, "[morphocuda] CUDA unavailable (%s): functionals stay on the reference builtins\n", mcu_last_error());
+        return;
+    }
+    int npatched = 0;
+    PATCH(Length, total); PATCH(Length, integrand); PATCH(Length, gradient);
+    PATCH(Area, total); PATCH(Area, integrand); PATCH(Area, gradient);
+    PATCH(VolumeEnclosed, total); PATCH(VolumeEnclosed, integrand); PATCH(VolumeEnclosed, gradient);
+    PATCH(Volume, total); PATCH(Volume, integrand); PATCH(Volume, gradient);
+    PATCH(AreaEnclosed, total); PATCH(AreaEnclosed, integrand);
+
+    int nhooks = 0;
+    nhooks += hook_writers("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Matrix", MORPHO_SETINDEX_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Matrix", MATRIX_SETCOLUMN_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Matrix", MATRIX_SETCOLUMN_METHOD_DEPRECATED, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Matrix", MORPHO_ACC_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Matrix", MATRIX_RESHAPE_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_writers("Mesh", MESH_SETVERTEXPOSITION_METHOD, WRAP_MESH_VERTS);
+    nhooks += hook_writers("Mesh", MESH_SETVERTEXMATRIX_METHOD, WRAP_MESH_VERTS);
+    nhooks += hook_writers("Mesh", MESH_ADDGRADE_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_REMOVEGRADE_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_RESETCONNECTIVITY_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_ADDSYMMETRY_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Sparse", SPARSE_SETROWINDICES_METHOD, WRAP_CONN_ALL);
+    nhooks += hook_writers("Sparse", MORPHO_SETINDEX_METHOD, WRAP_CONN_ALL);
+
+    object probe;
+    memset(&probe, 0, sizeof(probe));
+    probe.type = OBJECT_MESH;
+    objecttypedefn *defn = object_getdefn(&probe);
+    if (defn && defn->freefn != mc_meshfree) { orig_meshfree = defn->freefn; defn->freefn = mc_meshfree; }
+
+    mc_ready = true;
+    if (mc_verbose) fprintf(stderr, "[morphocuda] ready: %d builtins re-pointed, %d writers hooked\n", npatched, nhooks);
+}
+
+void morphocuda_finalize(void) {
+    mc_ready = false;
+    while (nmirrors > 0) mirror_drop(nmirrors - 1);
+    mcu_finalize();
+}
