@@ -14,7 +14,9 @@ A "step" is one pass of the hot path over the mesh: `Area.gradient(m)` followed 
 N > 1 (launched by torchrun, one rank per GPU): weak scaling — the global sphere has N x 10M
 triangles (f = round(707 sqrt N)) and is partitioned by contiguous element ranges across the
 ranks (the reference's own scheme, functional_binbounds functional.c:863-879); vertices shared
-between ranks get their partial gradient rows exchanged over NCCL and summed in fixed rank order.
+between ranks get their partial gradient rows pushed into the peers' receive buffers over NVLink peer
+memory (CUDA IPC, morpho_b200/csrc/mcu_halo.cu) and summed in fixed rank order; NCCL only carries the
+set-up and the max-over-ranks of the timings.
 """
 from __future__ import annotations
 
@@ -189,6 +191,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL prints its version) must not get in front of the one JSON line: everything that writes to
+    # file descriptor 1 goes to stderr, the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
@@ -222,13 +229,16 @@ def run_ours(args):
     nout = vert.size
     g_area = torch.empty(nout, dtype=torch.float64, device="cuda")
     g_vol = torch.empty(nout, dtype=torch.float64, device="cuda")
-    exch = part.make_exchange(torch, dist) if world > 1 else None
+    exch = None
+    if world > 1:
+        from morpho_b200.partition import PeerExchange
+        exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, two kernels per exchange, no collective call
 
     def step_device():
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
         if exch is not None:
-            exch(g_area, g_vol)                   # shared-vertex rows: NCCL all-gather + fixed-order sum
+            exch(g_area, g_vol)                   # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
 
     def barrier():
         if world > 1:
@@ -244,7 +254,7 @@ def run_ours(args):
         sampler.start()
         sampler.lines.clear()
     launches0 = L.mcu_launch_count()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record(stream)
@@ -256,20 +266,27 @@ def run_ours(args):
         ev[k][2].record(stream)
         if exch is not None:
             exch(g_area, g_vol)
+        ev[k][3].record(stream)
     e_end.record(stream)
     barrier()
     launches = L.mcu_launch_count() - launches0
     ms_total = e_start.elapsed_time(e_end)
     ms_area = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
     ms_vol = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
+    ms_exch = float(np.mean([ev[k][2].elapsed_time(ev[k][3]) for k in range(args.steps)]))
     # nvidia-smi cannot sample faster than ~100 ms: when the timed region is shorter than that, keep the SAME
     # load running (untimed) until a few samples exist, so the clocks line describes the kernels under load
-    if rank == 0:
-        t_load = time.time()
-        while len(sampler.lines) < 6 and time.time() - t_load < 3.0:
-            for _ in range(50):
-                step_device()
-            torch.cuda.synchronize()
+    # (every rank runs the same number of steps: the shared-vertex exchange pairs up launches across ranks)
+    t_load = time.time()
+    for _ in range(60):
+        for _ in range(50):
+            step_device()
+        torch.cuda.synchronize()
+        more = torch.tensor([1 if (rank == 0 and len(sampler.lines) < 6 and time.time() - t_load < 3.0) else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(more, 0)
+        if int(more.item()) == 0:
+            break
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -280,8 +297,14 @@ def run_ours(args):
 
     def step_e2e():
         _lib.check(L.mcu_mesh_set_vertices(mesh._h, hv.data_ptr()))
-        _lib.check(L.mcu_eval(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, ha.data_ptr()))
-        _lib.check(L.mcu_eval(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, hg.data_ptr()))
+        if exch is None:
+            _lib.check(L.mcu_eval(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, ha.data_ptr()))
+            _lib.check(L.mcu_eval(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, hg.data_ptr()))
+        else:                                             # partitioned: complete the shared rows before the read-back
+            step_device()
+            ha.copy_(g_area, non_blocking=True)
+            hg.copy_(g_vol, non_blocking=True)
+            stream.synchronize()
 
     e2e_steps = 1 if args.quick else max(3, min(args.steps, 10))
     for _ in range(0 if args.quick else 2):
@@ -296,11 +319,13 @@ def run_ours(args):
     ms_e2e = e2s.elapsed_time(e2e_) / e2e_steps
     checksum = float(ha[:3].sum() + hg[:3].sum())
 
+    if exch is not None and exch.status() != 0:
+        raise RuntimeError("halo exchange: a peer did not arrive in time")
     # ---- max over ranks ---------------------------------------------------------------------
-    times = torch.tensor([ms_total, ms_e2e, ms_area, ms_vol], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms_total, ms_e2e, ms_area, ms_vol, ms_exch], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_area, ms_vol = [float(x) for x in times.cpu()]
+    ms_total, ms_e2e, ms_area, ms_vol, ms_exch = [float(x) for x in times.cpu()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,9 +353,9 @@ def run_ours(args):
         "config": {"workload": f"icosphere f={f} ({nel_global} triangles global, {nel_local} per GPU), radial perturbation 1%, seed 12345; "
                                "step = Area.gradient + VolumeEnclosed.gradient (2 element-evals per triangle)",
                    "inputs": "larger than L2 (vertex matrix 120 MB + ring tables 101 MB + gradient 120 MB per functional)",
-                   "partition": "contiguous element ranges per GPU; shared-vertex rows all-gathered over NCCL" if world > 1 else "single GPU",
+                   "partition": "contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) and summed in rank order" if world > 1 else "single GPU",
                    "gradient_path": "persistent patch kernel: bulk-async (TMA) staging of vertex runs into a 3-stage shared-memory ring, one consumer thread per owned vertex walks its ring (owner computes, no atomics)",
-                   "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol}},
+                   "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol, "shared_row_exchange": ms_exch if world > 1 else 0.0}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(vert.nbytes), "d2h_bytes_per_step": int(2 * nout * 8),
                 "ms_per_step": ms_e2e, "steps": e2e_steps, "checksum": checksum},
@@ -342,7 +367,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(vert, conn)
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -152,6 +152,28 @@ int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const dou
 /* ---- element partition across GPUs: functional_binbounds (functional.c:863-879) ---- */
 int mcu_binbounds(int nel, int nbins, int *bounds);
 
+/* ---- multi-GPU (one process per GPU): completion of the gradient rows of vertices shared between ranks.
+ *      Elements are partitioned in contiguous id ranges (mcu_binbounds); the reference's analogue is the merge of the
+ *      per-thread gradient matrices with matrix_axpy (functional.c:1106-1119).  The exchange runs over NVLink peer
+ *      memory (CUDA IPC), not through a collective library: see morpho_b200/csrc/mcu_halo.cu.
+ *        shared_local[n_shared]        local ids of the vertices other ranks also touch, ascending global id
+ *        peer_ptr[world+1], peer_pos[] per peer q the positions (in shared_local) of the vertices shared with q,
+ *                                      ascending global id — the same order on both sides of a pair
+ *        max_m                         longest pair list over all pairs (agreed by all ranks)
+ *        contrib_ptr[n_shared+1], contrib_rank[], contrib_k[]
+ *                                      per shared vertex the sharing ranks in ascending order (own rank included, k = -1)
+ *                                      and the vertex's index k in the (that rank, this rank) pair list
+ *      ncomp = doubles exchanged per vertex (number of gradients x dim). ---- */
+typedef struct mcu_halo mcu_halo;
+mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_shared, const int *shared_local, const int *peer_ptr,
+                          const int *peer_pos, int max_m, const int *contrib_ptr, const int *contrib_rank,
+                          const int *contrib_k);
+int mcu_halo_export(mcu_halo *h, unsigned char handle[64]);          /* IPC handle of this rank's receive block */
+int mcu_halo_connect(mcu_halo *h, const unsigned char *handles);     /* world x 64 bytes, rank order */
+int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim);   /* asynchronous, library stream */
+int mcu_halo_status(mcu_halo *h);                                    /* 0 ok, 1 a peer timed out (synchronises) */
+int mcu_halo_destroy(mcu_halo *h);
+
 /* ---- measurement helpers (bench.py): CUDA events on the library stream ---- */
 int mcu_timer_start(void);
 int mcu_timer_stop(float *ms);

@@ -91,6 +91,12 @@ def lib():
         "mcu_device_malloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "mcu_device_free": (C.c_int, [vp]),
         "mcu_flush_l2": (C.c_int, []),
+        "mcu_halo_create": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
+        "mcu_halo_export": (C.c_int, [vp, vp]),
+        "mcu_halo_connect": (C.c_int, [vp, vp]),
+        "mcu_halo_exchange": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "mcu_halo_status": (C.c_int, [vp]),
+        "mcu_halo_destroy": (C.c_int, [vp]),
         "mcu_debug_patch_profile": (C.c_int, [vp]),
         "mcu_debug_patch_plan": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_long), vp, vp, vp]),
     }

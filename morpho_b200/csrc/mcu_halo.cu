@@ -1,0 +1,218 @@
+// mcu_halo.cu — completion of the gradient rows of vertices shared between GPUs, over NVLink peer memory.
+//
+// Multi-GPU evaluation partitions the ELEMENTS in contiguous id ranges, the reference's own scheme
+// (functional_binbounds, functional.c:863-879; there every thread fills a private full-size gradient matrix which is
+// merged with matrix_axpy, functional.c:1092-1135).  Here every rank (one process per GPU) computes partial
+// gradient rows for the vertices its elements touch; rows of vertices touched by several ranks have to be summed.
+//
+// No collective library call sits on this path.  Every rank owns one device block
+//     [ flags: int[world] | recv[2][world][max_m][ncomp] doubles ]
+// exported with cudaIpcGetMemHandle and mapped by all peers (NVLink / NVSwitch P2P):
+//   k_halo_push     each (peer q, k) pair stores this rank's partial row of the k-th vertex shared with q straight
+//                   into q's recv[parity][rank][k] (remote stores); the last CTA to finish fences and raises
+//                   flags[rank] = epoch on every peer;
+//   k_halo_combine  waits until all peers' flags reached the epoch, then sums, per shared vertex, the contributions
+//                   of all sharing ranks in ASCENDING RANK ORDER (own partial included at its place) and writes the
+//                   completed row back — the same order on every rank, so shared rows end up bitwise identical
+//                   everywhere and the result is deterministic.
+// Two receive buffers alternate (parity = epoch & 1): a rank can be at most one exchange ahead of a peer, because
+// finishing exchange e needs every peer's flag e, which a peer raises only after it finished combining e-1.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "mcu_host.h"
+
+extern long g_mcu_launches;
+
+struct mcu_halo {
+    int rank = 0, world = 1, ncomp = 0, n_shared = 0, max_m = 0, n_pairs = 0;
+    int epoch = 0;
+    // plan (device)
+    int *d_shared_local = nullptr;   // n_shared local vertex ids (ascending global id)
+    int *d_peer_ptr = nullptr;       // world+1 offsets into d_peer_pos
+    int *d_peer_pos = nullptr;       // positions in the shared list, per peer, ascending global id
+    int *d_contrib_ptr = nullptr;    // n_shared+1
+    int *d_contrib_rank = nullptr;   // sharing ranks, ascending (own rank included)
+    int *d_contrib_k = nullptr;      // index in the (rank, me) pair list; -1 for my own partial
+    // the exported block and the peers' mappings
+    unsigned char *d_block = nullptr;
+    size_t block_bytes = 0, recv_off = 0;
+    std::vector<void *> peer_block;  // world pointers (own block at [rank])
+    void **d_peer_block = nullptr;   // device copy
+    unsigned *d_counter = nullptr;
+    unsigned *d_status = nullptr;    // bit 0: a peer did not show up in time
+};
+
+#define HALO_MAXGRAD 4
+struct HaloGrads {
+    double *g[HALO_MAXGRAD];
+};
+
+__global__ void k_halo_push(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
+                            const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
+                            size_t recv_off, int rank, int world, int max_m, int ncomp, int parity, int n_pairs,
+                            unsigned *counter, int epoch) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_pairs) {
+        int q = 0;
+        while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
+        int k = t - peer_ptr[q];
+        int v = shared_local[peer_pos[t]];
+        double *dst = (double *) ((unsigned char *) peer_block[q] + recv_off) +
+                      (((size_t) parity * world + rank) * max_m + k) * ncomp;
+        for (int gi = 0; gi < ngrad; gi++)
+            for (int c = 0; c < dim; c++) dst[gi * dim + c] = grads.g[gi][(size_t) v * dim + c];   // remote stores
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < world; q++)
+                if (q != rank) ((volatile int *) peer_block[q])[rank] = epoch;    // "my rows of exchange `epoch` have landed"
+        }
+    }
+}
+
+__global__ void k_halo_combine(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
+                               const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank,
+                               const int *__restrict__ contrib_k, unsigned char *block, size_t recv_off, int rank, int world,
+                               int max_m, int ncomp, int parity, int n_shared, int epoch, unsigned *status) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        volatile int *flags = (volatile int *) block;
+        int good = 1;
+        long long t0 = clock64();
+        for (int q = 0; q < world && good; q++) {
+            if (q == rank) continue;
+            while (flags[q] < epoch) {
+                if (clock64() - t0 > 4000000000LL) { good = 0; break; }   // ~2 s: a peer is gone; do not hang the GPU
+                __nanosleep(64);
+            }
+        }
+        ok = good;
+        if (!good) atomicOr(status, 1u);
+    }
+    __syncthreads();
+    if (!ok) return;
+    __threadfence_system();
+    const double *recv = (const double *) (block + recv_off);
+    const int ncols = ngrad * dim;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_shared * ncols; t += gridDim.x * blockDim.x) {
+        int i = t / ncols, col = t - i * ncols, gi = col / dim, c = col - gi * dim;
+        int v = shared_local[i];
+        double own = grads.g[gi][(size_t) v * dim + c], sum = 0.0;
+        for (int j = contrib_ptr[i]; j < contrib_ptr[i + 1]; j++) {
+            int q = contrib_rank[j], k = contrib_k[j];
+            double x = (k < 0) ? own : __ldcv(recv + (((size_t) parity * world + q) * max_m + k) * ncomp + col);
+            sum = __dadd_rn(sum, x);                  // ascending rank order, identical on every sharing rank
+        }
+        grads.g[gi][(size_t) v * dim + c] = sum;
+    }
+}
+
+static int *upload_ints(const int *h, size_t n) {
+    int *d = nullptr;
+    if (cudaMalloc((void **) &d, sizeof(int) * (n ? n : 1)) != cudaSuccess) return nullptr;
+    if (n && cudaMemcpy(d, h, sizeof(int) * n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+
+extern "C" mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_shared, const int *shared_local,
+                                     const int *peer_ptr, const int *peer_pos, int max_m, const int *contrib_ptr,
+                                     const int *contrib_rank, const int *contrib_k) {
+    if (rank < 0 || world < 1 || rank >= world || ncomp < 1 || n_shared < 0 || max_m < 0) { mcu_set_error("bad halo arguments"); return nullptr; }
+    mcu_halo *h = new mcu_halo();
+    h->rank = rank; h->world = world; h->ncomp = ncomp; h->n_shared = n_shared; h->max_m = max_m;
+    h->n_pairs = peer_ptr[world];
+    h->d_shared_local = upload_ints(shared_local, (size_t) n_shared);
+    h->d_peer_ptr = upload_ints(peer_ptr, (size_t) world + 1);
+    h->d_peer_pos = upload_ints(peer_pos, (size_t) h->n_pairs);
+    h->d_contrib_ptr = upload_ints(contrib_ptr, (size_t) n_shared + 1);
+    h->d_contrib_rank = upload_ints(contrib_rank, (size_t) contrib_ptr[n_shared]);
+    h->d_contrib_k = upload_ints(contrib_k, (size_t) contrib_ptr[n_shared]);
+    h->recv_off = 256;
+    h->block_bytes = h->recv_off + sizeof(double) * 2 * (size_t) world * (size_t) (max_m ? max_m : 1) * ncomp;
+    bool ok = h->d_shared_local && h->d_peer_ptr && h->d_peer_pos && h->d_contrib_ptr && h->d_contrib_rank && h->d_contrib_k &&
+              cudaMalloc((void **) &h->d_block, h->block_bytes) == cudaSuccess &&
+              cudaMemset(h->d_block, 0, h->block_bytes) == cudaSuccess &&
+              cudaMalloc((void **) &h->d_counter, 64) == cudaSuccess && cudaMemset(h->d_counter, 0, 64) == cudaSuccess &&
+              cudaMalloc((void **) &h->d_peer_block, sizeof(void *) * world) == cudaSuccess;
+    if (!ok) { mcu_set_error("halo allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
+    h->d_status = h->d_counter + 4;
+    h->peer_block.assign((size_t) world, nullptr);
+    h->peer_block[rank] = h->d_block;
+    return h;
+}
+
+extern "C" int mcu_halo_export(mcu_halo *h, unsigned char handle[64]) {
+    if (!h) return MCU_ERR_ARGS;
+    cudaIpcMemHandle_t ipc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaError_t e = cudaIpcGetMemHandle(&ipc, h->d_block);
+    if (e != cudaSuccess) { mcu_set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
+    memcpy(handle, &ipc, 64);
+    return MCU_OK;
+}
+
+extern "C" int mcu_halo_connect(mcu_halo *h, const unsigned char *handles) {
+    if (!h || !handles) return MCU_ERR_ARGS;
+    for (int q = 0; q < h->world; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + 64 * (size_t) q, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { mcu_set_error("cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); return MCU_ERR_CUDA; }
+        h->peer_block[q] = p;
+    }
+    if (cudaMemcpy(h->d_peer_block, h->peer_block.data(), sizeof(void *) * h->world, cudaMemcpyHostToDevice) != cudaSuccess) return MCU_ERR_CUDA;
+    return MCU_OK;
+}
+
+extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim) {
+    if (!h || ngrad < 1 || ngrad > HALO_MAXGRAD || ngrad * dim > h->ncomp) { mcu_set_error("bad halo exchange arguments"); return MCU_ERR_ARGS; }
+    if (h->world == 1) return MCU_OK;
+    HaloGrads g;
+    for (int i = 0; i < HALO_MAXGRAD; i++) g.g[i] = i < ngrad ? dev_grads[i] : nullptr;
+    cudaStream_t st = mcu_stream();
+    h->epoch++;
+    int parity = h->epoch & 1;
+    int nb = (h->n_pairs + 255) / 256;
+    if (nb < 1) nb = 1;
+    k_halo_push<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block, h->recv_off,
+                                    h->rank, h->world, h->max_m, h->ncomp, parity, h->n_pairs, h->d_counter, h->epoch);
+    int nc = (h->n_shared * ngrad * dim + 255) / 256;
+    nc = nc < 1 ? 1 : (nc > 296 ? 296 : nc);
+    k_halo_combine<<<nc, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k,
+                                       h->d_block, h->recv_off, h->rank, h->world, h->max_m, h->ncomp, parity, h->n_shared, h->epoch,
+                                       h->d_status);
+    g_mcu_launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { mcu_set_error("halo launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
+    return MCU_OK;
+}
+
+/* 0 = all exchanges so far completed; 1 = a peer did not arrive in time (synchronises the stream) */
+extern "C" int mcu_halo_status(mcu_halo *h) {
+    if (!h) return MCU_ERR_ARGS;
+    unsigned s = 0;
+    if (cudaStreamSynchronize(mcu_stream()) != cudaSuccess) return MCU_ERR_CUDA;
+    if (cudaMemcpy(&s, h->d_status, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return MCU_ERR_CUDA;
+    return (int) s;
+}
+
+extern "C" int mcu_halo_destroy(mcu_halo *h) {
+    if (!h) return MCU_OK;
+    cudaStreamSynchronize(mcu_stream());
+    for (int q = 0; q < h->world; q++)
+        if (q != h->rank && h->peer_block[q]) cudaIpcCloseMemHandle(h->peer_block[q]);
+    cudaFree(h->d_shared_local); cudaFree(h->d_peer_ptr); cudaFree(h->d_peer_pos);
+    cudaFree(h->d_contrib_ptr); cudaFree(h->d_contrib_rank); cudaFree(h->d_contrib_k);
+    cudaFree(h->d_block); cudaFree(h->d_counter); cudaFree(h->d_peer_block);
+    delete h;
+    return MCU_OK;
+}

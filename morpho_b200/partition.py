@@ -22,7 +22,7 @@ import numpy as np
 
 from . import meshgen as mg
 
-__all__ = ["binbounds", "RankMesh", "build_rank_mesh", "partition_arrays", "shared_vertices"]
+__all__ = ["binbounds", "RankMesh", "build_rank_mesh", "partition_arrays", "shared_vertices", "halo_plan", "PeerExchange"]
 
 
 def binbounds(nel: int, nbins: int) -> np.ndarray:
@@ -46,6 +46,7 @@ class RankMesh:
     shared_local: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # local ids of shared vertices
     shared_slot: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))    # their row in the exchange buffer
     n_slots: int = 0             # rows of the exchange buffer (all vertices shared by >= 2 ranks)
+    rims: list = field(default_factory=list)   # per rank: sorted global ids it may share (superset of its shared ids)
 
     @property
     def n_shared(self):
@@ -119,6 +120,8 @@ def partition_arrays(vert: np.ndarray, conn: np.ndarray, world: int):
                             np.ascontiguousarray(vert[gids]), np.ascontiguousarray(np.sort(loc, axis=1))))
         touched.append(gids)
     s_all = shared_vertices(touched)
+    for rm in out:
+        rm.rims = touched
     return [_finish(rm, s_all) for rm in out]
 
 
@@ -165,4 +168,94 @@ def build_rank_mesh(f: int, rank: int, world: int, amplitude: float = 0.01, seed
     dist.all_gather(allr, pad)
     rims = [a.cpu().numpy()[: int(s.item())] for a, s in zip(allr, sizes)]
     s_all = shared_vertices(rims)
+    rm.rims = rims
     return _finish(rm, s_all)
+
+
+def halo_plan(rm: RankMesh) -> dict:
+    """Index arrays of the peer-memory exchange (include/morpho_cuda.h, mcu_halo_create) for one rank.
+
+    Every pair of ranks (r, q) agrees on the list of vertices they share, in ascending global id; entry k of
+    that list is where r's partial row lands in q's receive buffer and vice versa.  Per shared vertex the
+    contributions are listed in ascending rank order (own partial at its place, k = -1): the summation order
+    is the same on every rank that holds the vertex, so the completed rows are bitwise identical everywhere.
+    All arrays are int32; everything is derived from the ranks' rim lists, which every rank knows."""
+    world, r = rm.world, rm.rank
+    order = np.argsort(rm.gids[rm.shared_local], kind="stable")
+    shared_local = rm.shared_local[order].astype(np.int32)
+    shared_gid = rm.gids[shared_local]
+    rims = [np.asarray(x, dtype=np.int64) for x in rm.rims]
+    common = [np.intersect1d(rims[r], rims[q]) if q != r else np.zeros(0, np.int64) for q in range(world)]
+    peer_ptr = np.zeros(world + 1, dtype=np.int32)
+    peer_pos = []
+    for q in range(world):
+        pos = np.searchsorted(shared_gid, common[q])
+        assert np.array_equal(shared_gid[pos], common[q]) if len(pos) else True
+        peer_pos.append(pos.astype(np.int32))
+        peer_ptr[q + 1] = peer_ptr[q] + len(pos)
+    max_m = 0
+    for a in range(world):
+        for b in range(a + 1, world):
+            max_m = max(max_m, len(np.intersect1d(rims[a], rims[b])))
+    # contributions per shared vertex: which ranks hold it, ascending, and where their row sits
+    member = np.zeros((world, len(shared_gid)), dtype=bool)
+    kidx = np.full((world, len(shared_gid)), -1, dtype=np.int64)
+    for q in range(world):
+        if q == r:
+            member[q] = True
+            continue
+        pos = peer_pos[q]
+        member[q, pos] = True
+        kidx[q, pos] = np.arange(len(pos))
+    counts = member.sum(axis=0)
+    contrib_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    qq, ii = np.nonzero(member)                       # row-major: sorted by rank, then vertex
+    o = np.lexsort((qq, ii))                          # by vertex, then ascending rank
+    contrib_rank = qq[o].astype(np.int32)
+    contrib_k = kidx[qq[o], ii[o]].astype(np.int32)
+    return dict(shared_local=np.ascontiguousarray(shared_local), peer_ptr=peer_ptr,
+                peer_pos=np.ascontiguousarray(np.concatenate(peer_pos) if peer_pos else np.zeros(0, np.int32)).astype(np.int32),
+                max_m=int(max_m), contrib_ptr=contrib_ptr, contrib_rank=np.ascontiguousarray(contrib_rank),
+                contrib_k=np.ascontiguousarray(contrib_k))
+
+
+class PeerExchange:
+    """Shared-vertex completion over NVLink peer memory (morpho_b200/csrc/mcu_halo.cu): two kernels per
+    exchange, no collective call on the data path.  ``torch.distributed`` (NCCL) is used once, to hand the
+    CUDA IPC handles of the receive blocks around."""
+
+    def __init__(self, rm: RankMesh, torch, dist, ngrad: int = 2):
+        import ctypes as C
+        from . import _lib
+        self.L, self.C, self._lib = _lib.lib(), C, _lib
+        self.rm, self.dim, self.ngrad = rm, rm.vert.shape[1], ngrad
+        pl = self.plan = halo_plan(rm)
+        self.h = self.L.mcu_halo_create(rm.rank, rm.world, ngrad * self.dim, len(pl["shared_local"]),
+                                        pl["shared_local"].ctypes.data, pl["peer_ptr"].ctypes.data, pl["peer_pos"].ctypes.data,
+                                        pl["max_m"], pl["contrib_ptr"].ctypes.data, pl["contrib_rank"].ctypes.data,
+                                        pl["contrib_k"].ctypes.data)
+        if not self.h:
+            raise RuntimeError("mcu_halo_create failed: " + self.L.mcu_last_error().decode())
+        mine = np.zeros(64, dtype=np.uint8)
+        _lib.check(self.L.mcu_halo_export(self.h, mine.ctypes.data))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(mine).to(dev)
+        allh = [torch.empty_like(t) for _ in range(rm.world)]
+        dist.all_gather(allh, t)
+        handles = np.ascontiguousarray(np.concatenate([a.cpu().numpy() for a in allh]))
+        _lib.check(self.L.mcu_halo_connect(self.h, handles.ctypes.data))
+        dist.barrier()
+        self._ptrs = (C.c_void_p * 4)()
+
+    def __call__(self, *grads):
+        for i, g in enumerate(grads):
+            self._ptrs[i] = g.data_ptr()
+        self._lib.check(self.L.mcu_halo_exchange(self.h, len(grads), self._ptrs, self.dim))
+
+    def status(self):
+        return self.L.mcu_halo_status(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.mcu_halo_destroy(self.h)
+            self.h = None

@@ -1,0 +1,85 @@
+"""GPU, world_size 2 (needs two GPUs on the box; skipped otherwise): element-partitioned Area / VolumeEnclosed
+gradients with the shared-vertex rows completed over NVLink peer memory (mcu_halo.cu), against the CPU oracle
+on the undivided mesh."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, f, q):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import morpho_b200 as mb
+        from morpho_b200 import _lib, meshgen as mg
+        from morpho_b200.partition import PeerExchange, build_rank_mesh
+        from oracle.oracle import FunctionalSpec, Oracle
+        mb.init(rank)
+        L = mb.lib()
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        _lib.check(L.mcu_set_stream(stream.cuda_stream))
+        rm = build_rank_mesh(f, rank, world, dist=dist, torch=torch)
+        mesh = mb.Mesh(rm.vert, faces=rm.conn)
+        grads = [torch.empty(rm.vert.size, dtype=torch.float64, device="cuda") for _ in range(2)]
+        ex = PeerExchange(rm, torch, dist, ngrad=2)
+        v, c = mg.icosphere(f)
+        v = mg.perturb_radially(v)
+        O = Oracle()
+        errs = []
+        for rep in range(3):                           # several exchanges: alternating receive buffers, epochs
+            for g, cls in zip(grads, (mb.Area, mb.VolumeEnclosed)):
+                d = cls()._desc()
+                _lib.check(L.mcu_eval_device(mesh._h, C.byref(d), None, _lib.MCU_GRADIENT, g.data_ptr()))
+            ex(*grads)
+            assert ex.status() == 0
+            for g, name in zip(grads, ("Area", "VolumeEnclosed")):
+                want = O.gradient(v, {2: c}, FunctionalSpec(name))[rm.gids]
+                got = g.cpu().numpy().reshape(-1, 3)
+                errs.append(np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max())
+        # shared rows bitwise identical on both ranks
+        sh = torch.zeros((rm.n_slots, 3), dtype=torch.float64, device="cuda")
+        sh[torch.as_tensor(rm.shared_slot, device="cuda")] = grads[0].view(-1, 3)[torch.as_tensor(rm.shared_local, device="cuda")]
+        allsh = [torch.zeros_like(sh) for _ in range(world)]
+        dist.all_gather(allsh, sh)
+        same = all(bool(torch.equal(allsh[r], sh)) for r in range(world)) if world == 2 else True
+        ex.close()
+        q.put((rank, max(errs), rm.n_shared, same))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partitioned_gradient_over_peer_memory():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 60, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, nshared, same in res:
+        assert err <= 1e-12, (rank, err)
+        assert nshared > 0 and same

@@ -104,3 +104,56 @@ def test_partitioned_gradient_with_exchange_gloo(world):
     for rank, err, nshared, same in res:
         assert err <= 1e-13, (rank, err)
         assert nshared > 0 and same
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_exchange_plan_emulated(oracle, world):
+    """Index logic of the NVLink peer-memory exchange (mcu_halo.cu), emulated with numpy in one process:
+    push every rank's partial rows into the peers' receive buffers as the plan says, combine in ascending
+    rank order, and compare with the gradient of the undivided mesh.  Shared rows must come out bitwise
+    identical on all ranks that hold them."""
+    from oracle.oracle import FunctionalSpec
+    from morpho_b200.partition import halo_plan
+    v, c = mg.icosphere(10)
+    v = mg.perturb_radially(v)
+    parts = partition_arrays(v, c, world)
+    spec = FunctionalSpec("Area")
+    want = oracle.gradient(v, {2: c}, spec)
+    plans = [halo_plan(p) for p in parts]
+    max_m = plans[0]["max_m"]
+    assert all(pl["max_m"] == max_m for pl in plans)
+    partial = [oracle.gradient(p.vert, {2: p.conn}, spec) for p in parts]
+    recv = [np.full((world, max(max_m, 1), 3), np.nan) for _ in range(world)]
+    for r, (p, pl) in enumerate(zip(parts, plans)):
+        assert np.all(np.diff(p.gids[pl["shared_local"]]) > 0)
+        for q in range(world):
+            pos = pl["peer_pos"][pl["peer_ptr"][q]: pl["peer_ptr"][q + 1]]
+            if q == r:
+                assert len(pos) == 0
+                continue
+            # both sides of the pair list the same vertices in the same order
+            posq = plans[q]["peer_pos"][plans[q]["peer_ptr"][r]: plans[q]["peer_ptr"][r + 1]]
+            np.testing.assert_array_equal(p.gids[pl["shared_local"][pos]], parts[q].gids[plans[q]["shared_local"][posq]])
+            recv[q][r, : len(pos)] = partial[r][pl["shared_local"][pos]]
+    done = []
+    for r, (p, pl) in enumerate(zip(parts, plans)):
+        g = partial[r].copy()
+        for i, vloc in enumerate(pl["shared_local"]):
+            s = np.zeros(3)
+            ranks = pl["contrib_rank"][pl["contrib_ptr"][i]: pl["contrib_ptr"][i + 1]]
+            ks = pl["contrib_k"][pl["contrib_ptr"][i]: pl["contrib_ptr"][i + 1]]
+            assert np.all(np.diff(ranks) > 0) and r in ranks and len(ranks) >= 2
+            for q, k in zip(ranks, ks):
+                s = s + (partial[r][vloc] if k < 0 else recv[r][q, k])
+            g[vloc] = s
+        assert not np.isnan(g).any()
+        err = np.linalg.norm(g - want[p.gids], axis=1).max() / np.linalg.norm(want, axis=1).max()
+        assert err <= 1e-13
+        done.append(g)
+    glob = {}
+    for r, (p, pl) in enumerate(zip(parts, plans)):
+        for vloc in pl["shared_local"]:
+            key = int(p.gids[vloc])
+            if key in glob:
+                assert np.array_equal(glob[key], done[r][vloc])      # bitwise identical on every sharing rank
+            glob[key] = done[r][vloc]
