@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmorpho_cuda.so")
+LIB_PATH = os.environ.get("MORPHO_CUDA_LIB", os.path.join(HERE, "lib", "libmorpho_cuda.so"))   # env: kernel-variant experiments
 
 MCU_OK, MCU_ERR_ARGS, MCU_ERR_ELNOTFOUND, MCU_ERR_DEGENERATE, MCU_ERR_VOLENCLZERO, \
     MCU_ERR_UNSUPPORTED, MCU_ERR_CUDA, MCU_ERR_ALLOC = range(8)

@@ -5,8 +5,11 @@
 #include <vector>
 
 #define MCU_PATCH_MAX_SLOTS 1024      // slot indices are 10 bit
-#define MCU_PATCH_MAX_OWNED 512       // one consumer thread per owned vertex, 16 consumer warps
-#define MCU_PATCH_DEFAULT_OWNED 512
+#ifndef PK_CONSUMER_WARPS
+#define PK_CONSUMER_WARPS 16
+#endif
+#define MCU_PATCH_MAX_OWNED (32 * PK_CONSUMER_WARPS)   // one consumer thread per owned vertex
+#define MCU_PATCH_DEFAULT_OWNED MCU_PATCH_MAX_OWNED
 #define MCU_PATCH_MAX_TAB_BYTES 24576 // staged table of one patch (ring entries + owned ids)
 
 // One patch = up to 512 "owned" vertices (their gradient rows are produced by this patch's pass) plus the
