@@ -248,7 +248,7 @@ def run_ours(args):
     exch = None
     if world > 1:
         from morpho_b200.partition import PeerExchange
-        exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, two kernels per exchange, no collective call
+        exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
 
     def step_device():
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))

@@ -8,13 +8,14 @@
 // No collective library call sits on this path.  Every rank owns one device block
 //     [ flags: int[world] | recv[2][world][max_m][ncomp] doubles ]
 // exported with cudaIpcGetMemHandle and mapped by all peers (NVLink / NVSwitch P2P):
-//   k_halo_push     each (peer q, k) pair stores this rank's partial row of the k-th vertex shared with q straight
-//                   into q's recv[parity][rank][k] (remote stores); the last CTA to finish fences and raises
-//                   flags[rank] = epoch on every peer;
-//   k_halo_combine  waits until all peers' flags reached the epoch, then sums, per shared vertex, the contributions
-//                   of all sharing ranks in ASCENDING RANK ORDER (own partial included at its place) and writes the
-//                   completed row back — the same order on every rank, so shared rows end up bitwise identical
-//                   everywhere and the result is deterministic.
+//   k_halo_exchange (ONE launch per exchange)
+//     push     each (peer q, k) pair stores this rank's partial row of the k-th vertex shared with q straight into
+//              q's recv[parity][rank][k] (remote stores); the last CTA to finish fences and raises flags[rank] = epoch
+//              on every peer;
+//     combine  waits until all peers' flags reached the epoch, then sums, per shared vertex, the contributions of all
+//              sharing ranks in ASCENDING RANK ORDER (own partial included at its place) and writes the completed row
+//              back — the same order on every rank, so shared rows end up bitwise identical everywhere and the
+//              result is deterministic.
 // Two receive buffers alternate (parity = epoch & 1): a rank can be at most one exchange ahead of a peer, because
 // finishing exchange e needs every peer's flag e, which a peer raises only after it finished combining e-1.
 #include <cstdio>
@@ -49,12 +50,18 @@ struct HaloGrads {
     double *g[HALO_MAXGRAD];
 };
 
-__global__ void k_halo_push(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
-                            const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
-                            size_t recv_off, int rank, int world, int max_m, int ncomp, int parity, int n_pairs,
-                            unsigned *counter, int epoch) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_pairs) {
+// One launch per exchange.  Phase 1 (push): every (peer q, k) pair stores this rank's partial row of the k-th vertex
+// shared with q straight into q's recv[parity][rank][k] (remote stores); one system-scope fence per CTA, and the last
+// CTA to get there raises flags[rank] = epoch on every peer.  Phase 2 (combine): every CTA waits until all peers'
+// flags reached the epoch — peers raise them independently of this grid, and the grid is small enough (<= 64 CTAs)
+// to be resident as a whole — then sums its share of the shared vertices in ascending rank order.
+__global__ void __launch_bounds__(256)
+k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
+                const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
+                const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank, const int *__restrict__ contrib_k,
+                unsigned char *block, size_t recv_off, int rank, int world, int max_m, int ncomp, int parity, int n_pairs,
+                int n_shared, unsigned *counter, unsigned *status, int epoch) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += gridDim.x * blockDim.x) {
         int q = 0;
         while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
         int k = t - peer_ptr[q];
@@ -64,9 +71,10 @@ __global__ void k_halo_push(HaloGrads grads, int ngrad, int dim, const int *__re
         for (int gi = 0; gi < ngrad; gi++)
             for (int c = 0; c < dim; c++) dst[gi * dim + c] = grads.g[gi][(size_t) v * dim + c];   // remote stores
     }
-    __threadfence_system();
     __syncthreads();
+    __shared__ int ok;
     if (threadIdx.x == 0) {
+        __threadfence_system();                        // cumulative: covers the block's stores ordered by the barrier
         unsigned done = atomicAdd(counter, 1u);
         if (done == gridDim.x - 1) {
             *counter = 0;
@@ -74,15 +82,6 @@ __global__ void k_halo_push(HaloGrads grads, int ngrad, int dim, const int *__re
             for (int q = 0; q < world; q++)
                 if (q != rank) ((volatile int *) peer_block[q])[rank] = epoch;    // "my rows of exchange `epoch` have landed"
         }
-    }
-}
-
-__global__ void k_halo_combine(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
-                               const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank,
-                               const int *__restrict__ contrib_k, unsigned char *block, size_t recv_off, int rank, int world,
-                               int max_m, int ncomp, int parity, int n_shared, int epoch, unsigned *status) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
         volatile int *flags = (volatile int *) block;
         int good = 1;
         long long t0 = clock64();
@@ -90,15 +89,15 @@ __global__ void k_halo_combine(HaloGrads grads, int ngrad, int dim, const int *_
             if (q == rank) continue;
             while (flags[q] < epoch) {
                 if (clock64() - t0 > 4000000000LL) { good = 0; break; }   // ~2 s: a peer is gone; do not hang the GPU
-                __nanosleep(64);
+                __nanosleep(32);
             }
         }
+        __threadfence_system();
         ok = good;
         if (!good) atomicOr(status, 1u);
     }
     __syncthreads();
     if (!ok) return;
-    __threadfence_system();
     const double *recv = (const double *) (block + recv_off);
     const int ncols = ngrad * dim;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_shared * ncols; t += gridDim.x * blockDim.x) {
@@ -181,16 +180,14 @@ extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grad
     cudaStream_t st = mcu_stream();
     h->epoch++;
     int parity = h->epoch & 1;
-    int nb = (h->n_pairs + 255) / 256;
-    if (nb < 1) nb = 1;
-    k_halo_push<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block, h->recv_off,
-                                    h->rank, h->world, h->max_m, h->ncomp, parity, h->n_pairs, h->d_counter, h->epoch);
-    int nc = (h->n_shared * ngrad * dim + 255) / 256;
-    nc = nc < 1 ? 1 : (nc > 296 ? 296 : nc);
-    k_halo_combine<<<nc, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k,
-                                       h->d_block, h->recv_off, h->rank, h->world, h->max_m, h->ncomp, parity, h->n_shared, h->epoch,
-                                       h->d_status);
-    g_mcu_launches += 2;
+    int work = h->n_pairs > h->n_shared * ngrad * dim ? h->n_pairs : h->n_shared * ngrad * dim;
+    int nb = (work + 255) / 256;
+    nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);             // small enough to be resident as a whole (the CTAs wait for peers)
+    k_halo_exchange<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
+                                        h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank,
+                                        h->world, h->max_m, h->ncomp, parity, h->n_pairs, h->n_shared, h->d_counter, h->d_status,
+                                        h->epoch);
+    g_mcu_launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mcu_set_error("halo launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
     return MCU_OK;

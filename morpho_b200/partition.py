@@ -220,7 +220,7 @@ def halo_plan(rm: RankMesh) -> dict:
 
 
 class PeerExchange:
-    """Shared-vertex completion over NVLink peer memory (morpho_b200/csrc/mcu_halo.cu): two kernels per
+    """Shared-vertex completion over NVLink peer memory (morpho_b200/csrc/mcu_halo.cu): one kernel per
     exchange, no collective call on the data path.  ``torch.distributed`` (NCCL) is used once, to hand the
     CUDA IPC handles of the receive blocks around."""
 
