@@ -249,9 +249,17 @@ def run_ours(args):
     if world > 1:
         from morpho_b200.partition import PeerExchange
         exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
+        if not args.no_fused_push:
+            exch.attach(mesh)                             # the gradient kernels store the shared rows into the peers' buffers themselves
+
+    fused = exch is not None and not args.no_fused_push
 
     def step_device():
+        if fused:
+            exch.bind(0)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
+        if fused:
+            exch.bind(1)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
         if exch is not None:
             exch(g_area, g_vol)                   # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
@@ -276,8 +284,12 @@ def run_ours(args):
     e_start.record(stream)
     for k in range(args.steps):
         ev[k][0].record(stream)
+        if fused:
+            exch.bind(0)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
         ev[k][1].record(stream)
+        if fused:
+            exch.bind(1)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
         ev[k][2].record(stream)
         if exch is not None:
@@ -400,6 +412,7 @@ def main():
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")
+    ap.add_argument("--no-fused-push", action="store_true", help="multi-GPU: push the shared rows in the exchange kernel instead of the gradient kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -171,6 +171,11 @@ mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_shared, const in
 int mcu_halo_export(mcu_halo *h, unsigned char handle[64]);          /* IPC handle of this rank's receive block */
 int mcu_halo_connect(mcu_halo *h, const unsigned char *handles);     /* world x 64 bytes, rank order */
 int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim);   /* asynchronous, library stream */
+/* fused mode: the patch gradient kernel of `m` stores the shared rows into the peers' buffers itself (column block
+ * `slot` of the exchanged row, chosen with mcu_halo_bind before each evaluation); mcu_halo_exchange then only raises
+ * the flags, waits for the peers and combines */
+int mcu_halo_attach(mcu_halo *h, mcu_mesh *m);
+int mcu_halo_bind(mcu_halo *h, int slot);
 int mcu_halo_status(mcu_halo *h);                                    /* 0 ok, 1 a peer timed out (synchronises) */
 int mcu_halo_destroy(mcu_halo *h);
 

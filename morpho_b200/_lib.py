@@ -96,6 +96,8 @@ def lib():
         "mcu_halo_connect": (C.c_int, [vp, vp]),
         "mcu_halo_exchange": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "mcu_halo_status": (C.c_int, [vp]),
+        "mcu_halo_attach": (C.c_int, [vp, vp]),
+        "mcu_halo_bind": (C.c_int, [vp, C.c_int]),
         "mcu_halo_destroy": (C.c_int, [vp]),
         "mcu_debug_patch_profile": (C.c_int, [vp]),
         "mcu_debug_patch_plan": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_long), vp, vp, vp]),

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "mcu_host.h"
+#include "mcu_patch.h"
 
 long g_mcu_launches = 0;
 
@@ -411,6 +412,20 @@ long mcu_result_size(mcu_mesh *m, const mcu_functional *f, int mode) {
     return -1;
 }
 
+}  // extern "C"
+int mcu_ensure_patches(mcu_mesh *m, int g) {
+    if (!m || g != 2 || m->dim != 3 || !m->conn[g].present) return MCU_ERR_UNSUPPORTED;
+    McuConn &c = m->conn[g];
+    if (c.patches) return MCU_OK;
+    cudaStream_t st = g_stream;
+    CK(cudaStreamSynchronize(st));
+    std::vector<double> hv((size_t) m->nv * 3);
+    CK(cudaMemcpy(hv.data(), m->d_vert, sizeof(double) * hv.size(), cudaMemcpyDeviceToHost));
+    c.patches = mcu_patchset_build(m->nv, c.nel, c.h_rix.data(), hv.data(), st);
+    return c.patches ? MCU_OK : MCU_ERR_UNSUPPORTED;
+}
+extern "C" {
+
 static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *d_out) {
     const int F = f->functional;
     const int g = functional_grade(m, f);
@@ -497,17 +512,16 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
             bool use_patch = patchable && (path == MCU_PATH_PATCH || (path == MCU_PATH_AUTO && m->conn[g].nel >= mcu_opt("patch_min_elements", 4096)));
             if (use_patch) {
                 McuConn &c = m->conn[g];
-                if (!c.patches) {
-                    CK(cudaStreamSynchronize(st));
-                    std::vector<double> hv((size_t) m->nv * 3);
-                    CK(cudaMemcpy(hv.data(), m->d_vert, sizeof(double) * hv.size(), cudaMemcpyDeviceToHost));
-                    c.patches = mcu_patchset_build(m->nv, c.nel, c.h_rix.data(), hv.data(), st);
-                    if (!c.patches) {
-                        if (path == MCU_PATH_PATCH) return MCU_ERR_UNSUPPORTED;
-                        use_patch = false;
-                    }
+                if (!c.patches && mcu_ensure_patches(m, g) != MCU_OK) {
+                    if (path == MCU_PATH_PATCH) return MCU_ERR_UNSUPPORTED;
+                    use_patch = false;
                 }
-                if (use_patch) { e = mcu_patch_gradient(F, *c.patches, m->d_vert, d_out, m->d_flags, st); break; }
+                if (use_patch) {
+                    McuHaloPush push;
+                    bool pushing = m->halo && mcu_halo_push_params(m->halo, m->halo_slot, m->dim, &push);
+                    e = mcu_patch_gradient(F, *c.patches, m->d_vert, d_out, m->d_flags, st, pushing ? &push : nullptr);
+                    break;
+                }
             }
             e = fast ? mcu_fast_gradient(p, v, d_out, m->d_flags, st) : mcu_strict_gradient(p, v, d_out, m->d_flags, st);
             break;

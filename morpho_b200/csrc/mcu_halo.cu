@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "mcu_host.h"
+#include "mcu_patch.h"
 
 extern long g_mcu_launches;
 
@@ -43,6 +44,10 @@ struct mcu_halo {
     void **d_peer_block = nullptr;   // device copy
     unsigned *d_counter = nullptr;
     unsigned *d_status = nullptr;    // bit 0: a peer did not show up in time
+    // host copies of the pair lists (for mcu_halo_attach) and the fused mode switch
+    std::vector<int> h_shared_local, h_peer_ptr, h_peer_pos;
+    bool fused = false;              // pushes ride in the patch gradient kernel; the exchange kernel only combines
+    mcu_mesh *mesh = nullptr;
 };
 
 #define HALO_MAXGRAD 4
@@ -74,10 +79,15 @@ k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ sha
     __syncthreads();
     __shared__ int ok;
     if (threadIdx.x == 0) {
-        __threadfence_system();                        // cumulative: covers the block's stores ordered by the barrier
-        unsigned done = atomicAdd(counter, 1u);
-        if (done == gridDim.x - 1) {
-            *counter = 0;
+        // n_pairs == 0 (fused mode): the rows were stored by the gradient kernels, which have completed; nothing of
+        // this grid has to be ordered before the flags, so one CTA raises them right away.
+        bool raise = (n_pairs == 0) ? (blockIdx.x == 0) : false;
+        if (n_pairs > 0) {
+            __threadfence_system();                    // cumulative: covers the block's stores ordered by the barrier
+            unsigned done = atomicAdd(counter, 1u);
+            if (done == gridDim.x - 1) { *counter = 0; raise = true; }
+        }
+        if (raise) {
             __threadfence_system();
             for (int q = 0; q < world; q++)
                 if (q != rank) ((volatile int *) peer_block[q])[rank] = epoch;    // "my rows of exchange `epoch` have landed"
@@ -89,10 +99,11 @@ k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ sha
             if (q == rank) continue;
             while (flags[q] < epoch) {
                 if (clock64() - t0 > 4000000000LL) { good = 0; break; }   // ~2 s: a peer is gone; do not hang the GPU
-                __nanosleep(32);
+                __nanosleep(20);
             }
         }
-        __threadfence_system();
+        // the received rows are read below with cache-bypassing loads (ld.cv) issued after the barrier that follows
+        // this flag observation: no further fence is needed on the acquiring side
         ok = good;
         if (!good) atomicOr(status, 1u);
     }
@@ -127,6 +138,9 @@ extern "C" mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_share
     mcu_halo *h = new mcu_halo();
     h->rank = rank; h->world = world; h->ncomp = ncomp; h->n_shared = n_shared; h->max_m = max_m;
     h->n_pairs = peer_ptr[world];
+    h->h_shared_local.assign(shared_local, shared_local + n_shared);
+    h->h_peer_ptr.assign(peer_ptr, peer_ptr + world + 1);
+    h->h_peer_pos.assign(peer_pos, peer_pos + h->n_pairs);
     h->d_shared_local = upload_ints(shared_local, (size_t) n_shared);
     h->d_peer_ptr = upload_ints(peer_ptr, (size_t) world + 1);
     h->d_peer_pos = upload_ints(peer_pos, (size_t) h->n_pairs);
@@ -185,7 +199,7 @@ extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grad
     nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);             // small enough to be resident as a whole (the CTAs wait for peers)
     k_halo_exchange<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
                                         h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank,
-                                        h->world, h->max_m, h->ncomp, parity, h->n_pairs, h->n_shared, h->d_counter, h->d_status,
+                                        h->world, h->max_m, h->ncomp, parity, h->fused ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status,
                                         h->epoch);
     g_mcu_launches += 1;
     cudaError_t e = cudaGetLastError();
@@ -202,8 +216,47 @@ extern "C" int mcu_halo_status(mcu_halo *h) {
     return (int) s;
 }
 
+/* Fused mode: from now on the patch gradient kernel of `m` (triangles) stores the rows of shared vertices into the
+ * peers' receive buffers itself, column block `slot` (mcu_halo_bind selects the slot before each evaluation), and
+ * mcu_halo_exchange only raises the flags, waits and combines. */
+extern "C" int mcu_halo_attach(mcu_halo *h, mcu_mesh *m) {
+    if (!h || !m) return MCU_ERR_ARGS;
+    int rc = mcu_ensure_patches(m, 2);
+    if (rc != MCU_OK) { mcu_set_error("halo attach: the mesh has no patch decomposition"); return rc; }
+    std::vector<int> vtx, peer, kk;
+    for (int q = 0; q < h->world; q++)
+        for (int t = h->h_peer_ptr[q]; t < h->h_peer_ptr[q + 1]; t++) {
+            vtx.push_back(h->h_shared_local[h->h_peer_pos[t]]);
+            peer.push_back(q);
+            kk.push_back(t - h->h_peer_ptr[q]);
+        }
+    rc = mcu_patchset_attach_push(m->conn[2].patches, m->nv, (int) vtx.size(), vtx.data(), peer.data(), kk.data(), mcu_stream());
+    if (rc != MCU_OK) { mcu_set_error("halo attach failed"); return rc; }
+    h->fused = true; h->mesh = m;
+    m->halo = h; m->halo_slot = 0;
+    return MCU_OK;
+}
+
+extern "C" int mcu_halo_bind(mcu_halo *h, int slot) {
+    if (!h || !h->mesh || slot < 0) return MCU_ERR_ARGS;
+    h->mesh->halo_slot = slot;
+    return MCU_OK;
+}
+
+bool mcu_halo_push_params(mcu_halo *h, int slot, int dim, McuHaloPush *out) {
+    if (!h || !h->fused || (slot + 1) * dim > h->ncomp) return false;
+    out->entries = nullptr;               // filled in by the launcher
+    out->peer_block = (void *const *) h->d_peer_block;
+    out->recv_off = h->recv_off;
+    out->rank = h->rank; out->world = h->world; out->max_m = h->max_m; out->ncomp = h->ncomp;
+    out->parity = (h->epoch + 1) & 1;     // the exchange that follows this evaluation
+    out->col0 = slot * dim;
+    return true;
+}
+
 extern "C" int mcu_halo_destroy(mcu_halo *h) {
     if (!h) return MCU_OK;
+    if (h->mesh && h->mesh->halo == h) h->mesh->halo = nullptr;
     cudaStreamSynchronize(mcu_stream());
     for (int q = 0; q < h->world; q++)
         if (q != h->rank && h->peer_block[q]) cudaIpcCloseMemHandle(h->peer_block[q]);

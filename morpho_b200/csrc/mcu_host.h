@@ -28,6 +28,8 @@ struct mcu_mesh {
     unsigned *d_flags = nullptr;
     double *d_result = nullptr;      // staging for mcu_eval (host-out) results
     size_t result_cap = 0;
+    struct mcu_halo *halo = nullptr; // multi-GPU: exchange whose pushes ride in the patch gradient kernel (mcu_halo_bind)
+    int halo_slot = 0;
 };
 
 struct mcu_field {
@@ -54,3 +56,6 @@ void mcu_host_transpose(int nv, int n, int nvper, const int *rix, const int *eid
 // patch decomposition (mcu_patch.cu)
 McuPatchSet *mcu_patchset_build(int nv, int nel, const int *h_rix, const double *h_vert, cudaStream_t st);
 void mcu_patchset_free(McuPatchSet *ps);
+int mcu_ensure_patches(mcu_mesh *m, int g);        // builds conn[g].patches if absent (MCU_ERR_UNSUPPORTED if it cannot)
+struct McuHaloPush;
+bool mcu_halo_push_params(struct mcu_halo *h, int slot, int dim, McuHaloPush *out);

@@ -18,8 +18,10 @@ bool mcu_strict_supports(int functional, int mode);
 
 // Shared-memory patch kernel for triangle meshes (Area / VolumeEnclosed gradients).
 struct McuPatchSet;
+struct McuHaloPush;
 cudaError_t mcu_patch_gradient(int functional, const McuPatchSet &ps, const double *d_vert, double *d_out,
-                               unsigned *flags, cudaStream_t st);
+                               unsigned *flags, cudaStream_t st, const McuHaloPush *push);
+int mcu_patchset_attach_push(McuPatchSet *ps, int nv, int n, const int *vertex, const int *peer, const int *k, cudaStream_t st);
 
 // All-pairs kernels.
 cudaError_t mcu_pairwise_launch(int n, int dim, const double *d_x, int kind, double cutoff, int mode,

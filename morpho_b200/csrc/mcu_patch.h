@@ -42,7 +42,9 @@ struct McuPatchDesc {     // 544 bytes
 };
 
 // Staged table of a patch (32-bit words):
-//   [0] n_owned [1] n_slices [2] n_ent [3] 0
+//   [0] n_owned [1] n_slices [2] index of the patch's 17 per-warp push offsets [3] number of push entries (both 0 unless a
+//       halo exchange is attached: rows of vertices shared with other GPUs are also stored into the peers' receive
+//       buffers, see mcu_halo.cu)
 //   [4 .. 4+32*n_slices)            global id of the owned vertex of every (slice, lane); -1 = idle lane
 //   [.. + round4(n_slices+1))       entry offset of every slice (relative to the entry array), last = n_ent
 //   n_ent 16-bit entries, sliced ELL: entry k of lane l of slice s at ents[off[s] + 32*k + l]
@@ -64,8 +66,24 @@ struct McuPatchPlan {
     long lds_wavefronts = 0, lds_wavefronts_ideal = 0;
 };
 
+// Push of shared rows from inside the gradient kernel (multi-GPU): where thread `thread` of a patch stores a copy
+// of its row — receive buffer of rank `peer`, row `k` of the (this rank, peer) pair list.
+struct McuPushEntry { int thread, peer, k, pad; };
+struct McuHaloPush {      // kernel parameter; entries == nullptr: no exchange attached
+    const McuPushEntry *entries;
+    const int *wptr;                 // per boundary patch 17 offsets into entries: entries of warp w = [wptr[w], wptr[w+1])
+    void *const *peer_block;         // device array: base of every rank's receive block
+    unsigned long long recv_off;     // byte offset of recv[][][][] in a block
+    int rank, world, max_m, ncomp, parity, col0;   // col0 = first column of this gradient in a row (slot * dim)
+};
+
 struct McuPatchSet {
     McuPatchPlan plan;               // headers + statistics (bulk arrays are dropped after upload)
+    std::vector<int> owned_gid;      // owner thread order: vertex of every (patch, slice, lane), -1 = idle lane
+    std::vector<long> own_ptr;       // per patch offset into owned_gid (n_patches + 1)
+    std::vector<int> tab_word_off;   // per patch: word offset of its table header in d_tab
+    McuPushEntry *d_push = nullptr;
+    int *d_push_wptr = nullptr;
     int n_patches = 0;
     McuPatchDesc *d_desc = nullptr;
     McuPatchRun *d_runs = nullptr;

@@ -252,6 +252,14 @@ class PeerExchange:
             self._ptrs[i] = g.data_ptr()
         self._lib.check(self.L.mcu_halo_exchange(self.h, len(grads), self._ptrs, self.dim))
 
+    def attach(self, mesh):
+        """Fused mode: the patch gradient kernel of ``mesh`` pushes the shared rows itself; call
+        ``bind(slot)`` before evaluating the gradient that occupies column block ``slot``."""
+        self._lib.check(self.L.mcu_halo_attach(self.h, mesh._h))
+
+    def bind(self, slot):
+        self._lib.check(self.L.mcu_halo_bind(self.h, slot))
+
     def status(self):
         return self.L.mcu_halo_status(self.h)
 

@@ -97,8 +97,9 @@ def _decode_patch(P, h):
     gids = tab[4: 4 + 32 * n_slices].view(np.int32)
     noff = (n_slices + 4) & ~3
     offs = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
-    ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(tab[2])]
-    assert offs[0] == 0 and offs[-1] == int(tab[2]) and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 128)
+    ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(offs[-1])]
+    assert int(tab[2]) == 0 and int(tab[3]) == 0              # push list of the multi-GPU exchange: none attached
+    assert offs[0] == 0 and len(ents) == offs[-1] and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 128)
     return slot_gid, gids, offs, ents
 
 
