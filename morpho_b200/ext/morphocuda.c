@@ -63,8 +63,9 @@ static void mc_log(const char *what, const char *detail) {
 
 /* ------------------------------------------------------------------ mirrors */
 
+static void fields_drop_for(mcu_mesh *m);
 static void mirror_drop(int i) {
-    if (mirrors[i].m) mcu_mesh_destroy(mirrors[i].m);
+    if (mirrors[i].m) { fields_drop_for(mirrors[i].m); mcu_mesh_destroy(mirrors[i].m); }
     mirrors[i] = mirrors[nmirrors - 1];
     nmirrors--;
 }
@@ -124,6 +125,49 @@ static mc_mirror *mirror_get(objectmesh *mesh, grade g) {
         }
     }
     return mr;
+}
+
+/* ------------------------------------------------------------------ field mirrors */
+
+/* Vertex (P1) fields only: one entry per vertex, psize doubles each, no finite-element space (field.c:419-434).
+ * The device copy is refreshed on EVERY evaluation: fields are written through pool Matrix objects that alias the
+ * store (field.c:309-327, 1128-1132), which the vertex-matrix hooks do not cover yet; the upload is small next to the
+ * finite-difference kernels it feeds. */
+#define MC_MAXFIELDS 32
+typedef struct { objectfield *fld; mc_mirror *owner; mcu_mesh *m; mcu_field *f; int psize, nv; } mc_fieldmirror;
+static mc_fieldmirror fields[MC_MAXFIELDS];
+static int nfields = 0;
+static long mc_stat_field_uploads = 0;
+
+static void fields_drop_for(mcu_mesh *m) {
+    for (int i = 0; i < nfields;) {
+        if (!m || fields[i].m == m) { mcu_field_destroy(fields[i].f); fields[i] = fields[--nfields]; }
+        else i++;
+    }
+}
+
+static bool field_is_vertex_field(objectfield *fld, objectmesh *mesh) {
+    if (!fld || fld->mesh != mesh || !MORPHO_ISNIL(fld->fnspc) || fld->ngrades < 1 || fld->dof[0] != 1) return false;
+    for (unsigned int g = 1; g < fld->ngrades; g++) if (fld->dof[g] != 0) return false;
+    if (fld->psize < 1 || fld->psize > 9) return false;
+    return fld->data.nels == (MatrixCount_t) mesh->vert->ncols * fld->psize;
+}
+
+static mcu_field *field_get(objectfield *fld, mc_mirror *mr) {
+    mc_fieldmirror *fm = NULL;
+    for (int i = 0; i < nfields; i++)
+        if (fields[i].fld == fld && fields[i].m == mr->m && fields[i].psize == (int) fld->psize && fields[i].nv == mr->nv) fm = &fields[i];
+    if (!fm) {
+        if (nfields == MC_MAXFIELDS) { mcu_field_destroy(fields[0].f); fields[0] = fields[--nfields]; }
+        fm = &fields[nfields];
+        fm->f = mcu_field_create(mr->m, (int) fld->psize);
+        if (!fm->f) return NULL;
+        fm->fld = fld; fm->m = mr->m; fm->owner = mr; fm->psize = (int) fld->psize; fm->nv = mr->nv;
+        nfields++;
+    }
+    if (mcu_field_set(fm->f, fld->data.elements) != MCU_OK) return NULL;
+    mc_stat_field_uploads++;
+    return fm->f;
 }
 
 /* ------------------------------------------------------------------ the veneers */
@@ -209,6 +253,145 @@ static bool mc_eval(vm *v, int nargs, value *args, int functional, grade g, int 
     mc_log("not accelerated:", mcu_last_error());
     return false;
 }
+
+/* Functionals that read their parameters from instance properties (the reference's *_prepareref functions:
+ * curvature 2940-2961, gradsq 3623-3642, nematic 3757-3791, nematicelectric 4008-4033). */
+static bool prop(objectinstance *self, const char *name, value *out) {
+    objectstring key = MORPHO_STATICSTRING((char *) name);
+    return objectinstance_getproperty(self, MORPHO_OBJECT(&key), out);
+}
+
+static bool mc_eval_props(vm *v, int nargs, value *args, int functional, int mode, value *out) {
+    functional_mapinfo info;
+    *out = MORPHO_NIL;
+    if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
+    if (!functional_validateargs(v, nargs, args, &info)) return true;
+    objectinstance *self = MORPHO_GETINSTANCE(MORPHO_SELF(args));
+    if (info.sel && info.sel->mode != SELECT_SOME) return false;
+    mcu_functional f;
+    memset(&f, 0, sizeof(f));
+    f.functional = functional;
+    f.ksplay = f.ktwist = f.kbend = 1.0;
+    value val;
+    objectfield *own[2] = {NULL, NULL};
+    grade g = 0;
+    if (functional == MCU_F_LINECURVATURESQ) {
+        g = 0;
+        if (prop(self, CURVATURE_INTEGRANDONLY_PROPERTY, &val)) f.integrandonly = MORPHO_ISTRUE(val);
+        if (mesh_has_symmetries(info.mesh, 1)) return false;
+    } else {
+        /* the field(s) the functional was constructed with */
+        if (!prop(self, FUNCTIONAL_FIELD_PROPERTY, &val)) return false;
+        if (functional == MCU_F_NEMATICELECTRIC) {
+            if (!MORPHO_ISLIST(val)) return false;
+            value a = MORPHO_NIL, b = MORPHO_NIL;
+            list_getelement(MORPHO_GETLIST(val), 0, &a);
+            list_getelement(MORPHO_GETLIST(val), 1, &b);
+            if (!MORPHO_ISFIELD(a) || !MORPHO_ISFIELD(b)) return false;      /* a Matrix as the electric field: reference path */
+            own[0] = MORPHO_GETFIELD(a); own[1] = MORPHO_GETFIELD(b);
+        } else {
+            if (!MORPHO_ISFIELD(val)) return false;
+            own[0] = MORPHO_GETFIELD(val);
+        }
+        if (functional == MCU_F_NORMSQ) g = 0;
+        else {
+            g = mesh_maxgrade(info.mesh);
+            if (prop(self, FUNCTIONAL_GRADE_PROPERTY, &val) && MORPHO_ISINTEGER(val) && MORPHO_GETINTEGERVALUE(val) > 0) g = MORPHO_GETINTEGERVALUE(val);
+            if (g != 2 && g != 3) return false;
+        }
+        if (functional == MCU_F_NEMATIC) {
+            if (prop(self, NEMATIC_KSPLAY_PROPERTY, &val) && MORPHO_ISNUMBER(val)) morpho_valuetofloat(val, &f.ksplay);
+            if (prop(self, NEMATIC_KTWIST_PROPERTY, &val) && MORPHO_ISNUMBER(val)) morpho_valuetofloat(val, &f.ktwist);
+            if (prop(self, NEMATIC_KBEND_PROPERTY, &val) && MORPHO_ISNUMBER(val)) morpho_valuetofloat(val, &f.kbend);
+            if (prop(self, NEMATIC_PITCH_PROPERTY, &val) && MORPHO_ISNUMBER(val)) { morpho_valuetofloat(val, &f.pitch); f.haspitch = 1; }
+        }
+        for (int i = 0; i < 2; i++) if (own[i] && !field_is_vertex_field(own[i], info.mesh)) return false;
+        if (mesh_has_symmetries(info.mesh, g)) return false;
+    }
+    f.grade = g;
+    mc_mirror *mr = mirror_get(info.mesh, functional == MCU_F_LINECURVATURESQ ? 1 : g);
+    if (!mr) return false;
+    if (functional == MCU_F_LINECURVATURESQ && !mesh_getconnectivityelement(info.mesh, 0, 1)) return false;
+    if (g > 0 && !mesh_getconnectivityelement(info.mesh, 0, g)) { morpho_runtimeerror(v, FUNC_ELNTFND, g); return true; }
+    for (int i = 0; i < 2; i++) if (own[i]) { f.field[i] = field_get(own[i], mr); if (!f.field[i]) return false; }
+    objectfield *wrtfield = NULL;
+    if (mode == MCU_FIELDGRADIENT) {
+        /* the Field argument is the one differentiated; it has to be one of the functional's own (functional.c:1454-1460) */
+        if (!info.field) return false;
+        if (info.field == own[0]) f.wrt = 0;
+        else if (info.field == own[1]) f.wrt = 1;
+        else return false;
+        wrtfield = info.field;
+    }
+    mcu_selection *sel = NULL;
+    if (info.sel) {
+        int *ids, n = selection_ids(info.sel, g, &ids);
+        if (n < 0) return false;
+        sel = mcu_selection_create(mr->m, g, n, ids);
+        free(ids);
+        if (!sel) return false;
+    }
+    int rc = MCU_OK;
+    objectmatrix *new = NULL;
+    objectfield *newf = NULL;
+    double total = 0.0;
+    long n = mcu_result_size(mr->m, &f, mode);
+    if (n < 0) rc = MCU_ERR_UNSUPPORTED;
+    else switch (mode) {
+        case MCU_TOTAL: rc = mcu_eval(mr->m, &f, sel, MCU_TOTAL, &total); break;
+        case MCU_INTEGRAND:
+            new = matrix_new(1, (MatrixIdx_t) n, false);
+            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
+            if (n > 0) rc = mcu_eval(mr->m, &f, sel, MCU_INTEGRAND, new->elements);
+            break;
+        case MCU_GRADIENT:
+            new = matrix_new(mr->dim, mr->nv, false);
+            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
+            rc = mcu_eval(mr->m, &f, sel, MCU_GRADIENT, new->elements);
+            break;
+        case MCU_FIELDGRADIENT:
+            newf = object_newfield(info.mesh, wrtfield->prototype, wrtfield->fnspc, wrtfield->dof);   /* functional.c:1449 */
+            if (!newf || (long) newf->data.nels != n) { if (newf) object_free((object *) newf); newf = NULL; morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
+            rc = mcu_eval(mr->m, &f, sel, MCU_FIELDGRADIENT, newf->data.elements);
+            break;
+        default: rc = MCU_ERR_UNSUPPORTED;
+    }
+    if (sel) mcu_selection_destroy(sel);
+    if (rc == MCU_OK) {
+        mc_stat_evals++;
+        if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
+        else { *out = MORPHO_OBJECT(new ? (object *) new : (object *) newf); morpho_bindobjects(v, 1, out); }
+        return true;
+    }
+    if (new) object_free((object *) new);
+    if (newf) object_free((object *) newf);
+    if (rc == -1) return true;
+    if (rc == MCU_ERR_ELNOTFOUND) { morpho_runtimeerror(v, FUNC_ELNTFND, g); return true; }
+    mc_log("not accelerated:", mcu_last_error());
+    return false;
+}
+
+#define MC_PVENEER(cls, FID, meth, MODE) \
+    static builtinfunction orig_##cls##_##meth = NULL; \
+    static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
+        value out; \
+        if (mc_eval_props(v, nargs, args, FID, MODE, &out)) return out; \
+        mc_stat_fallbacks++; \
+        return orig_##cls##_##meth(v, nargs, args); \
+    }
+#define MC_FIELDFUNCTIONAL(cls, FID) \
+    MC_PVENEER(cls, FID, total, MCU_TOTAL) \
+    MC_PVENEER(cls, FID, integrand, MCU_INTEGRAND) \
+    MC_PVENEER(cls, FID, gradient, MCU_GRADIENT) \
+    MC_PVENEER(cls, FID, fieldgradient, MCU_FIELDGRADIENT)
+
+MC_FIELDFUNCTIONAL(GradSq, MCU_F_GRADSQ)
+MC_FIELDFUNCTIONAL(NormSq, MCU_F_NORMSQ)
+MC_FIELDFUNCTIONAL(Nematic, MCU_F_NEMATIC)
+MC_FIELDFUNCTIONAL(NematicElectric, MCU_F_NEMATICELECTRIC)
+MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, total, MCU_TOTAL)
+MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, integrand, MCU_INTEGRAND)
+MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, gradient, MCU_GRADIENT)
 
 #define MC_VENEER(cls, FID, GRADE, meth, MODE) \
     static builtinfunction orig_##cls##_##meth = NULL; \
@@ -314,11 +497,12 @@ static void mc_meshfree(object *obj) {
 
 /* ------------------------------------------------------------------ script-visible helpers */
 
-/* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference] */
+/* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference, field uploads] */
 static value mc_stats(vm *v, int nargs, value *args) {
-    value vals[4] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
-                     MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks)};
-    objectlist *l = object_newlist(4, vals);
+    value vals[5] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
+                     MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks),
+                     MORPHO_INTEGER((int) mc_stat_field_uploads)};
+    objectlist *l = object_newlist(5, vals);
     if (!l) return MORPHO_NIL;
     return morpho_wrapandbind(v, (object *) l);
 }
@@ -343,6 +527,11 @@ void morphocuda_initialize(void) {
     PATCH(VolumeEnclosed, total); PATCH(VolumeEnclosed, integrand); PATCH(VolumeEnclosed, gradient);
     PATCH(Volume, total); PATCH(Volume, integrand); PATCH(Volume, gradient);
     PATCH(AreaEnclosed, total); PATCH(AreaEnclosed, integrand);
+    PATCH(GradSq, total); PATCH(GradSq, integrand); PATCH(GradSq, gradient); PATCH(GradSq, fieldgradient);
+    PATCH(NormSq, total); PATCH(NormSq, integrand); PATCH(NormSq, gradient); PATCH(NormSq, fieldgradient);
+    PATCH(Nematic, total); PATCH(Nematic, integrand); PATCH(Nematic, gradient); PATCH(Nematic, fieldgradient);
+    PATCH(NematicElectric, total); PATCH(NematicElectric, integrand); PATCH(NematicElectric, gradient); PATCH(NematicElectric, fieldgradient);
+    PATCH(LineCurvatureSq, total); PATCH(LineCurvatureSq, integrand); PATCH(LineCurvatureSq, gradient);
 
     int nhooks = 0;
     nhooks += hook_writers("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF);
@@ -373,5 +562,6 @@ void morphocuda_initialize(void) {
 void morphocuda_finalize(void) {
     mc_ready = false;
     while (nmirrors > 0) mirror_drop(nmirrors - 1);
+    fields_drop_for(NULL);
     mcu_finalize();
 }

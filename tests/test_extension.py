@@ -54,13 +54,13 @@ def test_extension_loads_and_is_inert_without_a_gpu(tmp_path):
     ref, _ = run(src, tmp_path, "stock.morpho")
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho")
     assert "CUDA unavailable" in err                 # loud, and nothing of ours computes on the CPU
-    assert new[-1].replace(" ", "") == "[0,0,0,0]"
+    assert new[-1].replace(" ", "") == "[0,0,0,0,0]"
     assert ref == new[:-1]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,tol", [("functionals_basic.morpho", 1e-12), ("catenoid_cg.morpho", 1e-9),
-                                      ("volume_constraint.morpho", 1e-9)])
+                                      ("volume_constraint.morpho", 1e-9), ("field_functionals.morpho", 1e-9)])
 def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
     src = script(name)
     ref, _ = run(src, tmp_path, "stock.morpho")
@@ -68,12 +68,14 @@ def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
                    {"MORPHO_CUDA_VERBOSE": "1"})
     assert "ready:" in err, err
     stats = [int(x) for x in NUM.findall(new[-1])]
-    evals, vert_uploads, conn_uploads, fallbacks = stats
+    evals, vert_uploads, conn_uploads, fallbacks, field_uploads = stats
     assert evals > 0, (stats, err)
     compare(ref, new[:-1], tol)
     # the mirror is re-uploaded only when the VM wrote to it: far fewer uploads than evaluations in the optimisers
-    if name != "functionals_basic.morpho":
+    if name in ("catenoid_cg.morpho", "volume_constraint.morpho"):
         assert vert_uploads < evals, stats
+    if name == "field_functionals.morpho":
+        assert fallbacks == 0 and field_uploads > 0, stats       # every call of the script ran on the GPU
 
 
 @pytest.mark.gpu
