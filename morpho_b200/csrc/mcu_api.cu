@@ -499,6 +499,13 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
     cudaError_t e = cudaSuccess;
     switch (mode) {
         case MCU_TOTAL:
+            // large triangle meshes: the patch kernel (coordinates staged once per patch, every triangle counted once)
+            if (fast && !sel && g == 2 && m->dim == 3 && (F == MCU_F_AREA || F == MCU_F_VOLUMEENCLOSED) &&
+                mcu_opt("gradient_path", MCU_PATH_AUTO) != MCU_PATH_GATHER && m->conn[g].nel >= mcu_opt("patch_min_elements", 4096) &&
+                mcu_ensure_patches(m, g) == MCU_OK) {
+                e = mcu_patch_total(F, *m->conn[g].patches, m->d_vert, d_out, m->d_flags, st);
+                break;
+            }
             e = fast ? mcu_fast_total(p, v, m->d_partials, d_out, st) : mcu_strict_total(p, v, m->d_partials, d_out, st);
             break;
         case MCU_INTEGRAND:

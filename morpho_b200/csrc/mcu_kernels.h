@@ -21,6 +21,7 @@ struct McuPatchSet;
 struct McuHaloPush;
 cudaError_t mcu_patch_gradient(int functional, const McuPatchSet &ps, const double *d_vert, double *d_out,
                                unsigned *flags, cudaStream_t st, const McuHaloPush *push);
+cudaError_t mcu_patch_total(int functional, const McuPatchSet &ps, const double *d_vert, double *d_out, unsigned *flags, cudaStream_t st);
 int mcu_patchset_attach_push(McuPatchSet *ps, int nv, int n, const int *vertex, const int *peer, const int *k, cudaStream_t st);
 
 // All-pairs kernels.

@@ -42,7 +42,7 @@ struct McuPatchDesc {     // 544 bytes
 };
 
 // Staged table of a patch (32-bit words):
-//   [0] n_owned [1] n_slices [2] index of the patch's 17 per-warp push offsets [3] number of push entries (both 0 unless a
+//   [0] index of the patch [1] n_slices [2] index of the patch's 17 per-warp push offsets [3] number of push entries (both 0 unless a
 //       halo exchange is attached: rows of vertices shared with other GPUs are also stored into the peers' receive
 //       buffers, see mcu_halo.cu)
 //   [4 .. 4+32*n_slices)            global id of the owned vertex of every (slice, lane); -1 = idle lane
@@ -84,6 +84,7 @@ struct McuPatchSet {
     std::vector<int> tab_word_off;   // per patch: word offset of its table header in d_tab
     McuPushEntry *d_push = nullptr;
     int *d_push_wptr = nullptr;
+    struct CompSum *d_partials = nullptr;   // totals: one compensated partial sum per (patch, consumer warp)
     int n_patches = 0;
     McuPatchDesc *d_desc = nullptr;
     McuPatchRun *d_runs = nullptr;

@@ -93,14 +93,15 @@ def _decode_patch(P, h):
     assert at == n_slots and n_slots <= 1024
     assert tab_bytes % 16 == 0 and tx == 24 * n_slots + tab_bytes
     tab = P["tab"][4 * tab_off: 4 * tab_off + tab_bytes // 4]
-    assert int(tab[0]) == n_owned and int(tab[1]) == n_slices and n_slices == (n_owned + 31) // 32
+    assert int(tab[1]) == n_slices and n_slices == (n_owned + 31) // 32
+    patch_index = int(tab[0])
     gids = tab[4: 4 + 32 * n_slices].view(np.int32)
     noff = (n_slices + 4) & ~3
     offs = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
     ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(offs[-1])]
     assert int(tab[2]) == 0 and int(tab[3]) == 0              # push list of the multi-GPU exchange: none attached
     assert offs[0] == 0 and len(ents) == offs[-1] and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 128)
-    return slot_gid, gids, offs, ents
+    return slot_gid, gids, offs, ents, patch_index
 
 
 @pytest.mark.parametrize("f,max_owned", [(3, 512), (12, 512), (30, 200), (30, 512)])
@@ -112,10 +113,11 @@ def test_patch_plan_is_a_valid_owner_computes_decomposition(L, oracle, f, max_ow
     nv = v.shape[0]
     tptr, tidx = oracle.transpose(nv, c)
     owned_count = np.zeros(nv, dtype=np.int64)
-    for h in P["hdr"]:
+    for hi, h in enumerate(P["hdr"]):
         n_owned, n_slices = int(h[H_N_OWNED]), int(h[H_N_SLICES])
         assert 0 < n_owned <= max_owned
-        slot_gid, gids, offs, ents = _decode_patch(P, h)
+        slot_gid, gids, offs, ents, pidx = _decode_patch(P, h)
+        assert pidx == hi
         assert np.all(gids[n_owned:] == -1) and np.all(gids[:n_owned] >= 0)
         assert np.all(np.diff(gids[:n_owned]) > 0)          # threads in ascending id order → coalesced row writes
         owned_count[gids[:n_owned]] += 1
@@ -152,6 +154,6 @@ def test_patch_plan_handles_isolated_vertices(L):
     P = _plan(L, np.ascontiguousarray(v), c)
     owned = []
     for h in P["hdr"]:
-        slot_gid, gids, offs, ents = _decode_patch(P, h)
+        slot_gid, gids, offs, ents, _ = _decode_patch(P, h)
         owned.extend(int(g) for g in gids if g >= 0)
     assert sorted(owned) == list(range(v.shape[0]))
