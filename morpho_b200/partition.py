@@ -22,7 +22,7 @@ import numpy as np
 
 from . import meshgen as mg
 
-__all__ = ["binbounds", "RankMesh", "build_rank_mesh", "partition_arrays", "shared_vertices", "halo_plan", "PeerExchange"]
+__all__ = ["binbounds", "RankMesh", "build_rank_mesh", "partition_arrays", "shared_vertices", "halo_plan", "PeerExchange", "reduce_total"]
 
 
 def binbounds(nel: int, nbins: int) -> np.ndarray:
@@ -267,3 +267,20 @@ class PeerExchange:
         if self.h:
             self.L.mcu_halo_destroy(self.h)
             self.h = None
+
+
+def reduce_total(local_total: float, torch, dist) -> float:
+    """Energy of an element-partitioned mesh: every element belongs to exactly one rank, so the total is the sum of
+    the ranks' totals.  The reference adds its per-thread partial sums in thread order (functional.c:962-996); here
+    the per-rank totals are all-gathered (one double each) and added in ascending rank order on every rank —
+    the same bits everywhere, independent of the collective's internal reduction order."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(local_total)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor([float(local_total)], dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    total = 0.0
+    for p in parts:
+        total += float(p.item())
+    return total

@@ -56,6 +56,12 @@ def _worker(rank, world, port, f, q):
                 want = O.gradient(v, {2: c}, FunctionalSpec(name))[rm.gids]
                 got = g.cpu().numpy().reshape(-1, 3)
                 errs.append(np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max())
+        # energies: per-rank totals (patch kernel) summed in rank order
+        from morpho_b200.partition import reduce_total
+        for cls, name in ((mb.Area, "Area"), (mb.VolumeEnclosed, "VolumeEnclosed")):
+            tot = reduce_total(cls().total(mesh), torch, dist)
+            ref = O.total(v, {2: c}, FunctionalSpec(name))
+            errs.append(abs(tot - ref) / abs(ref))
         # shared rows bitwise identical on both ranks
         sh = torch.zeros((rm.n_slots, 3), dtype=torch.float64, device="cuda")
         sh[torch.as_tensor(rm.shared_slot, device="cuda")] = grads[0].view(-1, 3)[torch.as_tensor(rm.shared_local, device="cuda")]

@@ -66,6 +66,12 @@ def _worker(rank, world, port, f, q):
             spec = FunctionalSpec(name)
             grads.append(torch.from_numpy(O.gradient(rm.vert, {2: rm.conn}, spec).ravel().copy()))
             want.append(O.gradient(v, {2: c}, spec)[rm.gids])
+        from morpho_b200.partition import reduce_total
+        for name in ("Area", "VolumeEnclosed"):
+            spec = FunctionalSpec(name)
+            tot = reduce_total(O.total(rm.vert, {2: rm.conn}, spec), torch, dist)
+            ref = O.total(v, {2: c}, spec)
+            assert abs(tot - ref) <= 1e-13 * abs(ref), (name, tot, ref)
         rm.make_exchange(torch, dist)(*grads)
         errs = []
         for g, w in zip(grads, want):
