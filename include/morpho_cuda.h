@@ -113,6 +113,11 @@ int mcu_mesh_get_vertices(mcu_mesh *m, double *host_vert);            /* D2H */
 double *mcu_mesh_vertices_device(mcu_mesh *m);                        /* device pointer of the mirror */
 int mcu_mesh_set_connectivity(mcu_mesh *m, int grade, int nel, const int *host_rix);
 int mcu_mesh_counts(const mcu_mesh *m, int *dim, int *nv, int nel[4]);
+/* Mesh.addgrade (mesh_addgrade, mesh.c:419-489): elements of grade g (1 or 2) from the next higher grade present, ids in
+ * the reference's order of first discovery; built on the device (sort + scan).  mcu_mesh_get_connectivity copies the
+ * incidence (nel * (g+1) ints) of any grade back. */
+int mcu_mesh_addgrade(mcu_mesh *m, int grade, int *nel_out);
+int mcu_mesh_get_connectivity(mcu_mesh *m, int grade, int *host_rix);
 /* vertex→element incidence as the reference builds it with sparse_transpose → cs_transpose
  * (sparse.c:1227-1244, mesh.c:663-685): tptr[nv+1], tidx[nel*(g+1)] element ids ascending per vertex. */
 int mcu_mesh_get_transpose(mcu_mesh *m, int grade, int *host_tptr, int *host_tidx);

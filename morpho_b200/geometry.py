@@ -11,6 +11,8 @@ reference objects' meaning (mesh.h:25-31, field.h:25-41, selection.h:22-31):
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib
@@ -114,18 +116,12 @@ class Mesh:
         higher = next((h for h in range(g + 1, self.dim + 1) if h in self._conn), None)
         if higher is None:
             return None
-        src = self._conn[higher]
-        n = g + 1
-        from itertools import combinations
-        combos = list(combinations(range(higher + 1), n))          # lexicographic counter order
-        cand = np.stack([src[:, list(c)] for c in combos], axis=1).reshape(-1, n).astype(np.int64)
-        base = np.int64(self.nv)
-        key = np.zeros(cand.shape[0], dtype=np.int64)
-        for k in range(n):
-            key = key * base + cand[:, k]
-        _, first = np.unique(key, return_index=True)
-        first.sort()                                                # first occurrence defines the id
-        self._set_grade(g, cand[first].astype(np.int32))
+        nel = C.c_int(0)
+        check(lib().mcu_mesh_addgrade(self._h, g, C.byref(nel)))     # sort + scan on the device (mcu_connect.cu)
+        out = np.zeros((nel.value, g + 1), dtype=np.int32)
+        if nel.value:
+            check(lib().mcu_mesh_get_connectivity(self._h, g, out.ctypes.data))
+        self._conn[g] = out
         return self._conn[g]
 
     def transpose(self, g):
