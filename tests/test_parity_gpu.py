@@ -255,3 +255,75 @@ def test_addgrade_on_device_matches_the_reference_bit_exactly(mb, oracle, refere
     want = oracle.edges_from(f)
     print(f"addgrade(1) on 9 996 980 triangles: device {t_dev:.2f}s (incl. read-back), oracle (sort based, C) {time.time() - t0:.2f}s")
     np.testing.assert_array_equal(edges, want)
+
+
+def test_patch_path_on_irregular_meshes(mb, oracle):
+    """The patch pipeline (gradient AND total) away from the closed, nicely numbered sphere: a surface with boundary
+    (open fans), a non-manifold edge (three sheets meeting), randomly permuted vertex numbering (runs of one or two
+    vertices), isolated vertices, and the error statuses raised from inside the patch kernel."""
+    from morpho_b200 import meshgen as mg
+    mb.set_option("patch_min_elements", 0)
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_PATCH)
+    try:
+        rng = np.random.Generator(np.random.PCG64(99))
+        meshes = []
+        v, f, _ = mg.disk(40, 3)                                   # boundary: open fans
+        v = v + 0.01 * rng.standard_normal(v.shape) + np.array([0.3, 0.2, 1.0])
+        meshes.append(("disk", v, f))
+        # three rectangular sheets sharing one edge line (non-manifold: 3 triangles per interior edge of the spine)
+        n = 24
+        sheets, vs = [], []
+        for k, ang in enumerate((0.0, 2.1, 4.0)):
+            u, w = np.meshgrid(np.arange(n + 1) / n, np.arange(1, n + 1) / n, indexing="ij")
+            vs.append(np.stack([w.ravel() * np.cos(ang), w.ravel() * np.sin(ang), u.ravel()], axis=1))
+        spine = np.stack([np.zeros(n + 1), np.zeros(n + 1), np.arange(n + 1) / n], axis=1)
+        vert = np.concatenate([spine] + vs) + np.array([1.0, 1.0, 0.5])
+        tris = []
+        for k in range(3):
+            base = (n + 1) + k * (n + 1) * n
+            idx = lambda i, j: np.where(j == 0, i, base + i * n + (j - 1))     # column 0 is the shared spine
+            I, J = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+            I, J = I.ravel(), J.ravel()
+            a, b, c2, d = idx(I, J), idx(I + 1, J), idx(I, J + 1), idx(I + 1, J + 1)
+            tris += [np.stack([a, b, c2], axis=1), np.stack([b, d, c2], axis=1)]
+        tri = np.sort(np.concatenate(tris).astype(np.int32), axis=1)
+        meshes.append(("book", vert + 0.003 * rng.standard_normal(vert.shape), tri))
+        vs2, fs2 = mg.icosphere(30)                                # random numbering: no consecutive-id locality
+        vs2 = mg.perturb_radially(vs2)
+        perm = rng.permutation(vs2.shape[0])
+        inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+        meshes.append(("permuted sphere", vs2[perm], np.sort(inv[fs2].astype(np.int32), axis=1)))
+        vi = np.concatenate([vs2, [[2.0, 2.0, 2.0], [3.0, -1.0, 0.5]]])     # isolated vertices
+        meshes.append(("isolated", vi, fs2))
+        for name, vv, ff in meshes:
+            vv, ff = np.ascontiguousarray(vv), np.ascontiguousarray(ff)
+            if name == "permuted sphere":
+                # by default such a numbering is refused by the patch planner (hundreds of two-vertex copies per patch)
+                # and AUTO falls back to the gather kernel ...
+                with pytest.raises(mb.MorphoError):
+                    mb.Area().gradient(mb.Mesh(vv, faces=ff))
+                mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+                g = mb.Area().gradient(mb.Mesh(vv, faces=ff))
+                assert rel_array(g, oracle.gradient(vv, {2: ff}, FunctionalSpec("Area")), rows=3) <= TOL_EXACT
+                mb.set_option("gradient_path", mb._lib.MCU_PATH_PATCH)
+                # ... but the kernel itself must cope: force it (patches with more than 64 runs, the overflow path)
+                mb.set_option("patch_max_avg_runs", 1000000)
+            m = mb.Mesh(vv, faces=ff)
+            for cls, fname in ((mb.Area, "Area"), (mb.VolumeEnclosed, "VolumeEnclosed")):
+                spec = FunctionalSpec(fname)
+                g0 = oracle.gradient(vv, {2: ff}, spec)
+                g = cls().gradient(m)
+                assert rel_array(g, g0, rows=3) <= TOL_EXACT, (name, fname)
+                t0 = oracle.total(vv, {2: ff}, spec)
+                assert abs(cls().total(m) - t0) <= TOL_EXACT * abs(t0), (name, fname)
+        # statuses from inside the patch kernel
+        vz = vs2.copy(); vz[fs2[100, 2]] = 0.0
+        with pytest.raises(mb.MorphoError) as ei:
+            mb.VolumeEnclosed().gradient(mb.Mesh(vz, faces=fs2))
+        assert ei.value.id == "VolEnclZero"
+        vd = vs2.copy(); vd[fs2[7, 1]] = vd[fs2[7, 0]]
+        assert mb.Area().gradient(mb.Mesh(vd, faces=fs2)) is None
+    finally:
+        mb.set_option("patch_min_elements", 4096)
+        mb.set_option("patch_max_avg_runs", 160)
+        mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
