@@ -78,21 +78,26 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_grad_gather(McuParams p, McuView 
     for (int q = v.tptr[vtx]; q < v.tptr[vtx + 1]; q++) {
         int ce = v.tidx[q];
         int e = v.eids ? v.eids[ce] : ce;
+        // fully unrolled with constant indices (guards instead of run-time trip counts and a select instead of
+        // g[corner]): the small arrays stay in registers — indexed dynamically they live in local memory
         int ids[MCU_MAXNV];
-        int corner = 0;
-        for (int j = 0; j < p.nvper; j++) {
-            ids[j] = v.rix[(size_t) e * p.nvper + j];
-            if (ids[j] == vtx) corner = j;
-        }
         double x[MCU_MAXNV][3], g[MCU_MAXNV][3];
-        for (int j = 0; j < p.nvper; j++) {
-            const double *xv = v.vert + (size_t) ids[j] * p.dim;
-            x[j][0] = xv[0];
-            x[j][1] = xv[1];
-            x[j][2] = (p.dim == 3 ? xv[2] : 0.0);
+#pragma unroll
+        for (int j = 0; j < MCU_MAXNV; j++) {
+            ids[j] = (j < p.nvper) ? v.rix[(size_t) e * p.nvper + j] : -1;
+            const double *xv = v.vert + (size_t) (ids[j] < 0 ? 0 : ids[j]) * p.dim;
+            x[j][0] = (j < p.nvper) ? xv[0] : 0.0;
+            x[j][1] = (j < p.nvper) ? xv[1] : 0.0;
+            x[j][2] = (j < p.nvper && p.dim == 3) ? xv[2] : 0.0;
         }
-        if (analytic_grad<F>(x, g, &myflags))
-            for (int k = 0; k < 3; k++) acc[k] += g[corner][k];
+        if (analytic_grad<F>(x, g, &myflags)) {
+#pragma unroll
+            for (int j = 0; j < MCU_MAXNV; j++) {
+                const bool mine = ids[j] == vtx;
+#pragma unroll
+                for (int k = 0; k < 3; k++) acc[k] += mine ? g[j][k] : 0.0;
+            }
+        }
     }
     for (int k = 0; k < p.dim; k++) out[(size_t) vtx * p.dim + k] = acc[k];
     if (myflags) atomicOr(flags, myflags);  // status word only; never data
