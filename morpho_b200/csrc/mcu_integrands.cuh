@@ -229,7 +229,10 @@ struct FTraits {
 // Gather one element's data.  ids: nvper vertex ids.
 template <int F>
 __device__ __forceinline__ void gather_elem(const McuParams &p, const McuView &v, const int *ids, ElemData &d) {
-    for (int j = 0; j < p.nvper; j++) {
+    // constant trip count with a guard: d.x stays in registers (a run-time trip count puts it in local memory)
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) {
+        if (j >= p.nvper) continue;
         const double *xv = v.vert + (size_t) ids[j] * p.dim;
         d.x[j][0] = xv[0];
         d.x[j][1] = xv[1];

@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_total(McuParams p, McuView v, Com
         int e = v.eids ? v.eids[ce] : ce;
         int ids[MCU_MAXNV];
         if (p.g == 0) ids[0] = e;
-        else for (int j = 0; j < p.nvper; j++) ids[j] = v.rix[(size_t) e * p.nvper + j];
+        else {
+#pragma unroll
+            for (int j = 0; j < MCU_MAXNV; j++) if (j < p.nvper) ids[j] = v.rix[(size_t) e * p.nvper + j];
+        }
         ElemData d;
         gather_elem<F>(p, v, ids, d);
         comp_add(acc, eval_integrand<F>(p, d));

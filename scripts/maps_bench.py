@@ -17,7 +17,7 @@ ms = C.c_float()
 peak = 6549.4
 for cls in (mb.Area, mb.VolumeEnclosed):
     d = cls()._desc()
-    for mode, name, bytes_per in ((_lib.MCU_TOTAL, "total", 24.0), (_lib.MCU_INTEGRAND, "integrand", 32.0), (_lib.MCU_GRADIENT, "gradient(patch)", 36.0), (_lib.MCU_GRADIENT, "gradient(gather)", 36.0)):
+    for mode, name, bytes_per in ((_lib.MCU_TOTAL, "total(patch)", 24.0), (_lib.MCU_TOTAL, "total(gather)", 24.0), (_lib.MCU_INTEGRAND, "integrand", 32.0), (_lib.MCU_GRADIENT, "gradient(patch)", 36.0), (_lib.MCU_GRADIENT, "gradient(gather)", 36.0)):
         mb.set_option("gradient_path", _lib.MCU_PATH_GATHER if "gather" in name else _lib.MCU_PATH_AUTO)
         for _ in range(3):
             _lib.check(L.mcu_eval_device(m._h, C.byref(d), None, mode, out.data_ptr()))
