@@ -26,6 +26,9 @@ template <int F>
 __global__ void __launch_bounds__(MCU_BLOCK) k_total(McuParams p, McuView v, CompSum *partials) {
     CompSum acc = {0.0, 0.0};
     const int stride = gridDim.x * MCU_BLOCK;
+    // unrolled: the gathers of several elements are in flight per thread (a single dependent id -> coordinate chain
+    // per iteration leaves the memory system idle)
+#pragma unroll 4
     for (int ce = blockIdx.x * MCU_BLOCK + threadIdx.x; ce < v.n; ce += stride) {
         int e = v.eids ? v.eids[ce] : ce;
         int ids[MCU_MAXNV];
