@@ -73,43 +73,70 @@ __device__ __forceinline__ void p1grad_tri(int dim, const double (*x)[3], int nv
     perpendicular(dim, s[2], s[1], t[0]);
     perpendicular(dim, s[0], s[2], t[1]);
     perpendicular(dim, s[1], s[0], t[2]);
+#pragma unroll
     for (int i = 0; i < nvals * dim; i++) out[i] = 0;
+#pragma unroll
     for (int j = 0; j < 3; j++)
+#pragma unroll
         for (int i = 0; i < nvals; i++)
+#pragma unroll
             for (int k = 0; k < dim; k++) out[i * dim + k] = out[i * dim + k] + vals[j * stride + i] * t[j][k];
 }
 
 // gradsq_evaluategradient3d (functional.c:3584-3620): rows (x_i - x_0)^T, rhs f_i - f_0, solved by
 // LU with partial pivoting in the order LAPACK's dgetf2 + dgetrs use (matrix.c:129-139).
 __device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, const double *vals, int stride, double *out) {
+    // Same operations in the same order as dgetf2 + dgetrs on the 3x3 system; the row exchanges are written as
+    // conditional swaps with constant indices (a run-time pivot index would put a[] and b[] in local memory).
     double a[9];  // column major Mt: Mt[r + 3 c] = (x_{r+1} - x_0)[c]
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++) a[r + 3 * c] = x[r + 1][c] - x[0][c];
     int piv[3];
+#pragma unroll
     for (int j = 0; j < 3; j++) {
         int p = j;
         double big = fabs(a[j + 3 * j]);
+#pragma unroll
         for (int i = j + 1; i < 3; i++)
             if (fabs(a[i + 3 * j]) > big) { big = fabs(a[i + 3 * j]); p = i; }
         piv[j] = p;
-        if (p != j)
-            for (int c = 0; c < 3; c++) { double tt = a[j + 3 * c]; a[j + 3 * c] = a[p + 3 * c]; a[p + 3 * c] = tt; }
+#pragma unroll
+        for (int i = j + 1; i < 3; i++)
+            if (p == i) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { double tt = a[j + 3 * c]; a[j + 3 * c] = a[i + 3 * c]; a[i + 3 * c] = tt; }
+            }
         double r = 1.0 / a[j + 3 * j];
+#pragma unroll
         for (int i = j + 1; i < 3; i++) a[i + 3 * j] *= r;
+#pragma unroll
         for (int c = j + 1; c < 3; c++)
+#pragma unroll
             for (int i = j + 1; i < 3; i++) a[i + 3 * c] -= a[i + 3 * j] * a[j + 3 * c];
     }
+#pragma unroll
     for (int v = 0; v < nvals; v++) {
         double b[3];
+#pragma unroll
         for (int j = 0; j < 3; j++) b[j] = vals[(j + 1) * stride + v] - vals[v];
+#pragma unroll
         for (int j = 0; j < 3; j++)
-            if (piv[j] != j) { double tt = b[j]; b[j] = b[piv[j]]; b[piv[j]] = tt; }
+#pragma unroll
+            for (int i = j + 1; i < 3; i++)
+                if (piv[j] == i) { double tt = b[j]; b[j] = b[i]; b[i] = tt; }
+#pragma unroll
         for (int j = 0; j < 3; j++)
+#pragma unroll
             for (int i = j + 1; i < 3; i++) b[i] -= b[j] * a[i + 3 * j];
+#pragma unroll
         for (int j = 2; j >= 0; j--) {
             b[j] /= a[j + 3 * j];
+#pragma unroll
             for (int i = 0; i < j; i++) b[i] -= b[j] * a[i + 3 * j];
         }
+#pragma unroll
         for (int k = 0; k < 3; k++) out[v * 3 + k] = b[k];
     }
 }
@@ -117,12 +144,15 @@ __device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, cons
 // nematic_bcintf / nematic_bcintfg (functional.c:3818-3834): exact barycentric integrals
 __device__ __forceinline__ double bcintf(int n, const double *f) {
     double sum = 0;
+#pragma unroll
     for (int i = 0; i < n; i++) sum += f[i];
     return sum / n;
 }
 __device__ __forceinline__ double bcintfg(int n, const double *f, const double *g) {
     double sum = 0;
+#pragma unroll
     for (int i = 0; i < n; i++) {
+#pragma unroll
         for (int j = 0; j < n; j++) sum += f[i] * g[j];
         sum += f[i] * g[i];
     }
@@ -130,25 +160,30 @@ __device__ __forceinline__ double bcintfg(int n, const double *f, const double *
 }
 
 // gradsq_integrand (functional.c:3657-3676): size * |grad q|_F^2
-__device__ __forceinline__ double gradsq_integrand(const McuParams &p, const ElemData &d) {
+__device__ __forceinline__ double gradsq_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+    const int g = nv - 1;
     double grad[MCU_MAXPSIZE * 3];
-    double size = elem_size(p.g, d.x);
-    if (p.g == 2) p1grad_tri(p.dim, d.x, p.psize0, &d.q[0][0], MCU_MAXPSIZE, grad);
-    else p1grad_tet(d.x, p.psize0, &d.q[0][0], MCU_MAXPSIZE, grad);
-    double gradnrm = vnorm(p.psize0 * p.dim, grad);
+    double size = elem_size(g, d.x);
+    if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
+    else p1grad_tet(d.x, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
+    double gradnrm = vnorm(ps * dim, grad);
     return gradnrm * gradnrm * size;
 }
 
 // nematic_integrand (functional.c:3837-3923): Frank energy with a P1 director
-__device__ __forceinline__ double nematic_integrand(const McuParams &p, const ElemData &d) {
-    int nv = p.nvper, dim = p.dim;
+__device__ __forceinline__ double nematic_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+    const int g = nv - 1;
     double gradnnraw[MCU_MAXPSIZE * 3], gradnn[9], curlnn[3];
+#pragma unroll
     for (int i = 0; i < 9; i++) gradnn[i] = 0.0;
-    for (int i = 0; i < p.psize0 * 3; i++) gradnnraw[i] = 0.0;
-    double size = elem_size(p.g, d.x);
-    if (p.g == 2) p1grad_tri(dim, d.x, p.psize0, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
-    else if (p.g == 3) p1grad_tet(d.x, p.psize0, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
+#pragma unroll
+    for (int i = 0; i < ps * 3; i++) gradnnraw[i] = 0.0;
+    double size = elem_size(g, d.x);
+    if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
+    else if (g == 3) p1grad_tet(d.x, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
+#pragma unroll
     for (int j = 0; j < 3; j++)
+#pragma unroll
         for (int i = 0; i < dim; i++) gradnn[3 * j + i] = gradnnraw[dim * j + i];
     double divnn = 0.0;
     for (int i = 0; i < 3; i++) divnn += gradnn[4 * i];
@@ -159,16 +194,20 @@ __device__ __forceinline__ double nematic_integrand(const McuParams &p, const El
                        2 * curlnn[0] * curlnn[1], 2 * curlnn[1] * curlnn[2], 2 * curlnn[2] * curlnn[0]};
     double cbnd[6] = {ctwst[1] + ctwst[2], ctwst[0] + ctwst[2], ctwst[0] + ctwst[1], -ctwst[3], -ctwst[4], -ctwst[5]};
     double nnt[3][MCU_MAXNV];
+#pragma unroll
     for (int i = 0; i < nv; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) nnt[j][i] = d.q[i][j];
     double integrals[6] = {bcintfg(nv, nnt[0], nnt[0]), bcintfg(nv, nnt[1], nnt[1]), bcintfg(nv, nnt[2], nnt[2]),
                            bcintfg(nv, nnt[0], nnt[1]), bcintfg(nv, nnt[1], nnt[2]), bcintfg(nv, nnt[2], nnt[0])};
     double splay, twist = 0.0, bend = 0.0, chol = 0.0;
     splay = 0.5 * p.ksplay * size * divnn * divnn;
+#pragma unroll
     for (int i = 0; i < 6; i++) { twist += ctwst[i] * integrals[i]; bend += cbnd[i] * integrals[i]; }
     twist *= 0.5 * p.ktwist * size;
     bend *= 0.5 * p.kbend * size;
     if (p.haspitch) {
+#pragma unroll
         for (int i = 0; i < 3; i++) chol += -2 * curlnn[i] * bcintf(nv, nnt[i]) * p.pitch;
         chol += (p.pitch * p.pitch);
         chol *= 0.5 * p.ktwist * size;
@@ -177,14 +216,16 @@ __device__ __forceinline__ double nematic_integrand(const McuParams &p, const El
 }
 
 // nematicelectric_integrand (functional.c:4053-4092): size * E_i E_j <n_i n_j>, E = grad(phi)
-__device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, const ElemData &d) {
-    int nv = p.nvper, dim = p.dim;
+__device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+    const int g = nv - 1;
     double ee[3] = {0.0, 0.0, 0.0};
-    double size = elem_size(p.g, d.x);
-    if (p.g == 2) p1grad_tri(dim, d.x, 1, d.phi, 1, ee);
-    else if (p.g == 3) p1grad_tet(d.x, 1, d.phi, 1, ee);
+    double size = elem_size(g, d.x);
+    if (g == 2) p1grad_tri(dim, d.x, 1, d.phi, 1, ee);
+    else if (g == 3) p1grad_tet(d.x, 1, d.phi, 1, ee);
     double nnt[3][MCU_MAXNV];
+#pragma unroll
     for (int j = 0; j < 3; j++)
+#pragma unroll
         for (int i = 0; i < nv; i++) nnt[j][i] = (j < dim ? d.q[i][j] : 0.0);
     double total = ee[0] * ee[0] * bcintfg(nv, nnt[0], nnt[0]) +
                    ee[1] * ee[1] * bcintfg(nv, nnt[1], nnt[1]) +
@@ -196,8 +237,10 @@ __device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, 
 }
 
 // One integrand evaluation on gathered data.  F is a compile-time functional id.
+// (nv, dim, ps) = vertices per element, coordinates per vertex, doubles per field entry: literal constants in the
+// shape-specialised kernels (everything below unrolls and the element data stays in registers), p's values otherwise.
 template <int F>
-__device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemData &d) {
+__device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
     if (F == MCU_F_LENGTH) return elem_size(1, d.x);
     if (F == MCU_F_AREAENCLOSED) {
 #ifdef MCU_STRICT
@@ -212,10 +255,10 @@ __device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemD
     if (F == MCU_F_AREA) return elem_size(2, d.x);
     if (F == MCU_F_VOLUMEENCLOSED) return volumeenclosed_of(d.x);
     if (F == MCU_F_VOLUME) return volume_of(d.x);
-    if (F == MCU_F_GRADSQ) return gradsq_integrand(p, d);
-    if (F == MCU_F_NEMATIC) return nematic_integrand(p, d);
-    if (F == MCU_F_NEMATICELECTRIC) return nematicelectric_integrand(p, d);
-    if (F == MCU_F_NORMSQ) return dotn(p.psize0, d.q[0], d.q[0]);  // normsq_integrand, functional.c:4149-4160
+    if (F == MCU_F_GRADSQ) return gradsq_integrand(p, d, nv, dim, ps);
+    if (F == MCU_F_NEMATIC) return nematic_integrand(p, d, nv, dim, ps);
+    if (F == MCU_F_NEMATICELECTRIC) return nematicelectric_integrand(p, d, nv, dim, ps);
+    if (F == MCU_F_NORMSQ) return dotn(ps, d.q[0], d.q[0]);  // normsq_integrand, functional.c:4149-4160
     return 0.0;
 }
 
@@ -228,18 +271,19 @@ struct FTraits {
 
 // Gather one element's data.  ids: nvper vertex ids.
 template <int F>
-__device__ __forceinline__ void gather_elem(const McuParams &p, const McuView &v, const int *ids, ElemData &d) {
+__device__ __forceinline__ void gather_elem(const McuParams &p, const McuView &v, const int *ids, ElemData &d, int nv, int dim, int ps) {
     // constant trip count with a guard: d.x stays in registers (a run-time trip count puts it in local memory)
 #pragma unroll
     for (int j = 0; j < MCU_MAXNV; j++) {
-        if (j >= p.nvper) continue;
-        const double *xv = v.vert + (size_t) ids[j] * p.dim;
+        if (j >= nv) continue;
+        const double *xv = v.vert + (size_t) ids[j] * dim;
         d.x[j][0] = xv[0];
         d.x[j][1] = xv[1];
-        d.x[j][2] = (p.dim == 3 ? xv[2] : 0.0);
+        d.x[j][2] = (dim == 3 ? xv[2] : 0.0);
         if (FTraits<F>::needs_q) {
-            const double *qv = v.f0 + (size_t) ids[j] * p.psize0;
-            for (int i = 0; i < p.psize0; i++) d.q[j][i] = qv[i];
+            const double *qv = v.f0 + (size_t) ids[j] * ps;
+#pragma unroll
+            for (int i = 0; i < ps; i++) d.q[j][i] = qv[i];
         }
         if (FTraits<F>::needs_phi) d.phi[j] = v.f1[ids[j]];
     }

@@ -22,9 +22,51 @@
 
 #define MCU_BLOCK 256
 
-template <int F>
+// Shape code of a kernel instantiation: 0 = generic (vertices per element, dimension and field width read from the
+// parameters at run time); otherwise nv | ps << 3 with dim = 3 — literal constants, so that every loop over them
+// unrolls and the gathered element data lives in registers instead of a local-memory stack frame.
+#define MCU_SHAPE(nv, ps) ((nv) | ((ps) << 3))
+template <int SH> struct Shape {
+    static __device__ __forceinline__ int nv(const McuParams &p) { return SH ? (SH & 7) : p.nvper; }
+    static __device__ __forceinline__ int dim(const McuParams &p) { return SH ? 3 : p.dim; }
+    static __device__ __forceinline__ int ps(const McuParams &p) { return SH ? (SH >> 3) : p.psize0; }
+};
+// element vertex `corner` (run-time) / component k, without run-time indexing of the register arrays
+__device__ __forceinline__ double elem_getx(const ElemData &d, int corner, int k) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) r = d.x[j][k];
+    return r;
+}
+__device__ __forceinline__ void elem_setx(ElemData &d, int corner, int k, double val) {
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) d.x[j][k] = val;
+}
+__device__ __forceinline__ double elem_getq(const ElemData &d, int corner, int i) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) r = d.q[j][i];
+    return r;
+}
+__device__ __forceinline__ void elem_setq(ElemData &d, int corner, int i, double val) {
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) d.q[j][i] = val;
+}
+__device__ __forceinline__ double elem_getphi(const ElemData &d, int corner) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) r = d.phi[j];
+    return r;
+}
+__device__ __forceinline__ void elem_setphi(ElemData &d, int corner, double val) {
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j == corner) d.phi[j] = val;
+}
+
+template <int F, int SH>
 __global__ void __launch_bounds__(MCU_BLOCK) k_total(McuParams p, McuView v, CompSum *partials) {
     CompSum acc = {0.0, 0.0};
+    const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps = Shape<SH>::ps(p);
     const int stride = gridDim.x * MCU_BLOCK;
     // unrolled: the gathers of several elements are in flight per thread (a single dependent id -> coordinate chain
     // per iteration leaves the memory system idle)
@@ -35,11 +77,11 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_total(McuParams p, McuView v, Com
         if (p.g == 0) ids[0] = e;
         else {
 #pragma unroll
-            for (int j = 0; j < MCU_MAXNV; j++) if (j < p.nvper) ids[j] = v.rix[(size_t) e * p.nvper + j];
+            for (int j = 0; j < MCU_MAXNV; j++) if (j < nv) ids[j] = v.rix[(size_t) e * nv + j];
         }
         ElemData d;
-        gather_elem<F>(p, v, ids, d);
-        comp_add(acc, eval_integrand<F>(p, d));
+        gather_elem<F>(p, v, ids, d, nv, dim, ps);
+        comp_add(acc, eval_integrand<F>(p, d, nv, dim, ps));
     }
     CompSum r = block_reduce<MCU_BLOCK>(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = r;
@@ -53,17 +95,21 @@ static __global__ void __launch_bounds__(MCU_BLOCK) k_total_finish(const CompSum
     if (threadIdx.x == 0) out[0] = r.s + r.c;
 }
 
-template <int F>
+template <int F, int SH>
 __global__ void __launch_bounds__(MCU_BLOCK) k_integrand(McuParams p, McuView v, double *out) {
     int ce = blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (ce >= v.n) return;
+    const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps = Shape<SH>::ps(p);
     int e = v.eids ? v.eids[ce] : ce;
     int ids[MCU_MAXNV];
     if (p.g == 0) ids[0] = e;
-    else for (int j = 0; j < p.nvper; j++) ids[j] = v.rix[(size_t) e * p.nvper + j];
+    else {
+#pragma unroll
+        for (int j = 0; j < MCU_MAXNV; j++) if (j < nv) ids[j] = v.rix[(size_t) e * nv + j];
+    }
     ElemData d;
-    gather_elem<F>(p, v, ids, d);
-    out[e] = eval_integrand<F>(p, d);
+    gather_elem<F>(p, v, ids, d, nv, dim, ps);
+    out[e] = eval_integrand<F>(p, d, nv, dim, ps);
 }
 
 template <int F>
@@ -112,10 +158,11 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_grad_gather(McuParams p, McuView 
 // Central differences with respect to the coordinates of one vertex, summed over the
 // incident elements in ascending id: frc = f0 + (fp - fm)/(2 eps) per coordinate
 // (functional_numericalgrad, functional.c:1142-1162).
-template <int F>
+template <int F, int SH>
 __global__ void __launch_bounds__(MCU_BLOCK) k_fd_grad(McuParams p, McuView v, double *out) {
     int vtx = blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (vtx >= p.nv) return;
+    const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps = Shape<SH>::ps(p);
     double acc[3] = {0.0, 0.0, 0.0};
     if (p.g == 0) {
         // vertex elements whose integrand does not depend on positions (NormSq): FD gives exact zeros
@@ -125,36 +172,43 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_grad(McuParams p, McuView v, d
             int e = v.eids ? v.eids[ce] : ce;
             int ids[MCU_MAXNV];
             int corner = 0;
-            for (int j = 0; j < p.nvper; j++) {
-                ids[j] = v.rix[(size_t) e * p.nvper + j];
+#pragma unroll
+            for (int j = 0; j < MCU_MAXNV; j++) {
+                if (j >= nv) continue;
+                ids[j] = v.rix[(size_t) e * nv + j];
                 if (ids[j] == vtx) corner = j;
             }
             ElemData d;
-            gather_elem<F>(p, v, ids, d);
-            for (int k = 0; k < p.dim; k++) {
-                double x0 = d.x[corner][k];
+            gather_elem<F>(p, v, ids, d, nv, dim, ps);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (k >= dim) continue;
+                double x0 = elem_getx(d, corner, k);
                 double eps = fdstepsize(x0);
-                d.x[corner][k] = x0 + eps;
-                double fp = eval_integrand<F>(p, d);
-                d.x[corner][k] = x0 - eps;
-                double fm = eval_integrand<F>(p, d);
-                d.x[corner][k] = x0;
+                elem_setx(d, corner, k, x0 + eps);
+                double fp = eval_integrand<F>(p, d, nv, dim, ps);
+                elem_setx(d, corner, k, x0 - eps);
+                double fm = eval_integrand<F>(p, d, nv, dim, ps);
+                elem_setx(d, corner, k, x0);
                 acc[k] = acc[k] + (fp - fm) / (2 * eps);
             }
         }
     }
-    for (int k = 0; k < p.dim; k++) out[(size_t) vtx * p.dim + k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) if (k < dim) out[(size_t) vtx * dim + k] = acc[k];
 }
 
 // Central differences with respect to the field degrees of freedom stored at one vertex
 // (functional_numericalfieldgrad, functional.c:1305-1328).
-template <int F>
+template <int F, int SH>
 __global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView v, double *out) {
     int vtx = blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (vtx >= p.nv) return;
-    const int ps = (p.wrt == 0 ? p.psize0 : p.psize1);
+    const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps0 = Shape<SH>::ps(p);
+    const int ps = (p.wrt == 0 ? ps0 : p.psize1);
     double acc[MCU_MAXPSIZE];
-    for (int i = 0; i < ps; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < MCU_MAXPSIZE; i++) acc[i] = 0.0;
     if (p.g == 0) {
         // grade-0 functional (NormSq): the element is the vertex itself
         bool selected = true;
@@ -162,14 +216,14 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView
         if (selected) {
             int ids[1] = {vtx};
             ElemData d;
-            gather_elem<F>(p, v, ids, d);
+            gather_elem<F>(p, v, ids, d, 1, dim, ps0);
             for (int i = 0; i < ps; i++) {
                 double f0 = d.q[0][i];
                 double eps = fdstepsize(f0);
                 d.q[0][i] = f0 + eps;
-                double fr = eval_integrand<F>(p, d);
+                double fr = eval_integrand<F>(p, d, 1, dim, ps0);
                 d.q[0][i] = f0 - eps;
-                double fl = eval_integrand<F>(p, d);
+                double fl = eval_integrand<F>(p, d, 1, dim, ps0);
                 d.q[0][i] = f0;
                 acc[i] += (fr - fl) / (2 * eps);
             }
@@ -180,26 +234,49 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView
             int e = v.eids ? v.eids[ce] : ce;
             int ids[MCU_MAXNV];
             int corner = 0;
-            for (int j = 0; j < p.nvper; j++) {
-                ids[j] = v.rix[(size_t) e * p.nvper + j];
+#pragma unroll
+            for (int j = 0; j < MCU_MAXNV; j++) {
+                if (j >= nv) continue;
+                ids[j] = v.rix[(size_t) e * nv + j];
                 if (ids[j] == vtx) corner = j;
             }
             ElemData d;
-            gather_elem<F>(p, v, ids, d);
-            for (int i = 0; i < ps; i++) {
-                double *slot = (p.wrt == 0 ? &d.q[corner][i] : &d.phi[corner]);
-                double f0 = *slot;
-                double eps = fdstepsize(f0);
-                *slot = f0 + eps;
-                double fr = eval_integrand<F>(p, d);
-                *slot = f0 - eps;
-                double fl = eval_integrand<F>(p, d);
-                *slot = f0;
-                acc[i] += (fr - fl) / (2 * eps);
+            gather_elem<F>(p, v, ids, d, nv, dim, ps0);
+            if (SH) {
+                // shape known at compile time: constant indices everywhere
+#pragma unroll
+                for (int i = 0; i < MCU_MAXPSIZE; i++) {
+                    if (i >= ps) continue;
+                    double f0 = (p.wrt == 0) ? elem_getq(d, corner, i) : elem_getphi(d, corner);
+                    double eps = fdstepsize(f0);
+                    if (p.wrt == 0) elem_setq(d, corner, i, f0 + eps); else elem_setphi(d, corner, f0 + eps);
+                    double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+                    if (p.wrt == 0) elem_setq(d, corner, i, f0 - eps); else elem_setphi(d, corner, f0 - eps);
+                    double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+                    if (p.wrt == 0) elem_setq(d, corner, i, f0); else elem_setphi(d, corner, f0);
+                    acc[i] += (fr - fl) / (2 * eps);
+                }
+            } else {
+                for (int i = 0; i < ps; i++) {
+                    double *slot = (p.wrt == 0 ? &d.q[corner][i] : &d.phi[corner]);
+                    double f0 = *slot;
+                    double eps = fdstepsize(f0);
+                    *slot = f0 + eps;
+                    double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+                    *slot = f0 - eps;
+                    double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+                    *slot = f0;
+                    acc[i] += (fr - fl) / (2 * eps);
+                }
             }
         }
     }
-    for (int i = 0; i < ps; i++) out[(size_t) vtx * ps + i] = acc[i];
+    if (SH) {
+#pragma unroll
+        for (int i = 0; i < MCU_MAXPSIZE; i++) if (i < ps) out[(size_t) vtx * ps + i] = acc[i];
+    } else {
+        for (int i = 0; i < ps; i++) out[(size_t) vtx * ps + i] = acc[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -215,10 +292,37 @@ static inline int mcu_total_grid(int n) {
 
 extern long g_mcu_launches;
 
+// Shape of the call, if one of the specialised instantiations fits (field functionals on 3-D triangles /
+// tetrahedra with the usual field widths); 0 = generic kernel.
+template <int F>
+static inline int mcu_shape_of(const McuParams &p) {
+    if (p.dim != 3 || (p.nvper != 3 && p.nvper != 4)) return 0;
+    if (F == MCU_F_NEMATIC || F == MCU_F_NEMATICELECTRIC) return p.psize0 == 3 ? MCU_SHAPE(p.nvper, 3) : 0;
+    if (F == MCU_F_GRADSQ) return (p.psize0 == 1 || p.psize0 == 3 || p.psize0 == 5) ? MCU_SHAPE(p.nvper, p.psize0) : 0;
+    return 0;
+}
+#define MCU_SHAPE_SWITCH(F, sh, LAUNCH) \
+    do { \
+        if constexpr (F == MCU_F_NEMATIC || F == MCU_F_NEMATICELECTRIC || F == MCU_F_GRADSQ) { \
+            if (sh == MCU_SHAPE(3, 3)) { LAUNCH(MCU_SHAPE(3, 3)); break; } \
+            if (sh == MCU_SHAPE(4, 3)) { LAUNCH(MCU_SHAPE(4, 3)); break; } \
+        } \
+        if constexpr (F == MCU_F_GRADSQ) { \
+            if (sh == MCU_SHAPE(3, 1)) { LAUNCH(MCU_SHAPE(3, 1)); break; } \
+            if (sh == MCU_SHAPE(4, 1)) { LAUNCH(MCU_SHAPE(4, 1)); break; } \
+            if (sh == MCU_SHAPE(3, 5)) { LAUNCH(MCU_SHAPE(3, 5)); break; } \
+            if (sh == MCU_SHAPE(4, 5)) { LAUNCH(MCU_SHAPE(4, 5)); break; } \
+        } \
+        LAUNCH(0); \
+    } while (0)
+
 template <int F>
 static cudaError_t run_total(const McuParams &p, const McuView &v, CompSum *partials, double *d_out, cudaStream_t st) {
     int blocks = mcu_total_grid(v.n);
-    k_total<F><<<blocks, MCU_BLOCK, 0, st>>>(p, v, partials);
+    const int sh = mcu_shape_of<F>(p);
+#define L_(S) k_total<F, S><<<blocks, MCU_BLOCK, 0, st>>>(p, v, partials)
+    MCU_SHAPE_SWITCH(F, sh, L_);
+#undef L_
     k_total_finish<<<1, MCU_BLOCK, 0, st>>>(partials, blocks, d_out);
     g_mcu_launches += 2;
     return cudaGetLastError();
@@ -227,7 +331,10 @@ static cudaError_t run_total(const McuParams &p, const McuView &v, CompSum *part
 template <int F>
 static cudaError_t run_integrand(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
     if (v.n > 0) {
-        k_integrand<F><<<(v.n + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out);
+        const int sh = mcu_shape_of<F>(p);
+#define L_(S) k_integrand<F, S><<<(v.n + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out)
+        MCU_SHAPE_SWITCH(F, sh, L_);
+#undef L_
         g_mcu_launches += 1;
     }
     return cudaGetLastError();
@@ -242,14 +349,20 @@ static cudaError_t run_grad_gather(const McuParams &p, const McuView &v, double 
 
 template <int F>
 static cudaError_t run_fd_grad(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
-    k_fd_grad<F><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out);
+    const int sh = mcu_shape_of<F>(p);
+#define L_(S) k_fd_grad<F, S><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out)
+    MCU_SHAPE_SWITCH(F, sh, L_);
+#undef L_
     g_mcu_launches += 1;
     return cudaGetLastError();
 }
 
 template <int F>
 static cudaError_t run_fd_fieldgrad(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
-    k_fd_fieldgrad<F><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out);
+    const int sh = mcu_shape_of<F>(p);
+#define L_(S) k_fd_fieldgrad<F, S><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out)
+    MCU_SHAPE_SWITCH(F, sh, L_);
+#undef L_
     g_mcu_launches += 1;
     return cudaGetLastError();
 }
