@@ -224,11 +224,12 @@ class PeerExchange:
     exchange, no collective call on the data path.  ``torch.distributed`` (NCCL) is used once, to hand the
     CUDA IPC handles of the receive blocks around."""
 
-    def __init__(self, rm: RankMesh, torch, dist, ngrad: int = 2):
+    def __init__(self, rm: RankMesh, torch, dist, ngrad: int = 2, dim: int = None):
         import ctypes as C
         from . import _lib
         self.L, self.C, self._lib = _lib.lib(), C, _lib
-        self.rm, self.dim, self.ngrad = rm, rm.vert.shape[1], ngrad
+        # dim = doubles per vertex row of the tensors exchanged (mesh dimension for vertex gradients, psize for field gradients)
+        self.rm, self.dim, self.ngrad = rm, (rm.vert.shape[1] if dim is None else int(dim)), ngrad
         pl = self.plan = halo_plan(rm)
         self.h = self.L.mcu_halo_create(rm.rank, rm.world, ngrad * self.dim, len(pl["shared_local"]),
                                         pl["shared_local"].ctypes.data, pl["peer_ptr"].ctypes.data, pl["peer_pos"].ctypes.data,

@@ -94,3 +94,77 @@ def test_partitioned_gradient_over_peer_memory():
     for rank, err, nshared, same in res:
         assert err <= 1e-12, (rank, err)
         assert nshared > 0 and same
+
+
+def _worker_tets(rank, world, port, n, q):
+    """Config 5 in miniature: a tetrahedral cube partitioned by element ranges; Volume gradient per rank, shared rows
+    completed by the (non-fused) peer-memory exchange; field gradient of GradSq likewise (5 doubles per vertex)."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import morpho_b200 as mb
+        from morpho_b200 import _lib, meshgen as mg
+        from morpho_b200.partition import PeerExchange, partition_arrays, reduce_total
+        from oracle.oracle import FunctionalSpec, Oracle
+        mb.init(rank)
+        L = mb.lib()
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        _lib.check(L.mcu_set_stream(stream.cuda_stream))
+        v, t = mg.tet_cube(n)
+        rng = np.random.Generator(np.random.PCG64(5))
+        v = v + 0.1 / n * rng.uniform(-1, 1, size=v.shape)
+        qf = rng.standard_normal((v.shape[0], 5))
+        rm = partition_arrays(v, t, world)[rank]
+        mesh = mb.Mesh(rm.vert, volumes=rm.conn)
+        O = Oracle()
+        errs = []
+        # vertex gradient of Volume: 3 doubles per shared vertex
+        ex3 = PeerExchange(rm, torch, dist, ngrad=1)
+        g = torch.from_numpy(mb.Volume().gradient(mesh).ravel().copy()).cuda()
+        ex3(g)
+        assert ex3.status() == 0
+        want = O.gradient(v, {3: t}, FunctionalSpec("Volume"))[rm.gids]
+        got = g.cpu().numpy().reshape(-1, 3)
+        errs.append(np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max())
+        tot = reduce_total(mb.Volume().total(mesh), torch, dist)
+        errs.append(abs(tot - O.total(v, {3: t}, FunctionalSpec("Volume"))) / tot)
+        ex3.close()
+        # field gradient of GradSq: rows of 5 doubles go through the same exchange (dim = 5 columns per vertex)
+        fld = mb.Field(mesh, qf[rm.gids])
+        fg = torch.from_numpy(mb.GradSq(fld).fieldgradient(fld, mesh).ravel().copy()).cuda()
+        ex5 = PeerExchange(rm, torch, dist, ngrad=1, dim=5)
+        ex5(fg)
+        assert ex5.status() == 0
+        wantf = O.fieldgradient(v, {3: t}, FunctionalSpec("GradSq", fields=[qf]), 0)[rm.gids]
+        gotf = fg.cpu().numpy().reshape(-1, 5)
+        errs.append(np.linalg.norm(gotf - wantf, axis=1).max() / np.linalg.norm(wantf, axis=1).max())
+        ex5.close()
+        q.put((rank, errs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partitioned_tet_mesh_over_peer_memory():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_tets, args=(r, world, port, 10, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        assert errs[0] <= 1e-12 and errs[1] <= 1e-12, (rank, errs)     # analytic gradient and total
+        assert errs[2] <= 2e-9, (rank, errs)                             # finite-difference field gradient
