@@ -15,6 +15,7 @@
 #   pkg/share/modules/*.morpho   copy of the reference's script modules so that
 #                                `import optimize` works on the GPU box
 #   home/.morphopackages    package list pointing at pkg/ (resources.c:246-273)
+#   reftests/                copy of the reference's test/{functionals,selection,field,mesh} (run on the GPU box too)
 # TEST INFRASTRUCTURE ONLY.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -64,6 +65,10 @@ gcc $CFLAGS $INC $DEFS -shared "$HERE/ref_harness.c" -o "$OUT/libmorpho_refharne
     -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$OBDIR" -Wl,-rpath-link,"$OBDIR" -lm
 
 cp -f "$REF"/modules/*.morpho "$OUT/pkg/share/modules/"
+# the reference's own golden-output tests of the hot path, so that the GPU box (which has no /root/reference) can run
+# them through the extension as well (tests/test_extension.py).  Build output only: oracle/_ref is never committed.
+rm -rf "$OUT/reftests"; mkdir -p "$OUT/reftests"
+for d in functionals selection field mesh; do cp -r "$REF/test/$d" "$OUT/reftests/$d"; done
 echo "$PKG" > "$OUT/home/.morphopackages"
 echo "$OBDIR" > "$OUT/openblas_dir.txt"
 echo "build_ref.sh: built $(ls "$OBJ"/*.o | wc -l) objects -> $OUT"

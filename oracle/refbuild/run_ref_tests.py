@@ -7,7 +7,9 @@ Mechanism of the reference's test/test.py (lines 44-47, 96-144) re-stated: every
 ``@error[Id]``.  (test.py itself needs the `colored` package, absent here.)
 
 Usage:  python oracle/refbuild/run_ref_tests.py [--dirs functionals mesh ...] [--json out.json]
-Needs /root/reference (dev container only).  TEST INFRASTRUCTURE ONLY.
+        [--root oracle/_ref/reftests] [--prepend "import morphocuda"]
+--root defaults to /root/reference/test (dev container); oracle/_ref/reftests is the copy build_ref.sh makes
+so that the suite also runs where the reference tree is absent.  TEST INFRASTRUCTURE ONLY.
 """
 import argparse
 import glob
@@ -37,7 +39,7 @@ def expected_of(path):
 
 
 def output_of(text):
-    lines = [re.sub(r"\x1b[^m]*m", "", l.rstrip()) for l in text.splitlines()]
+    lines = [re.sub(r"\x1b[^m]*m", "", l.rstrip()) for l in text.splitlines() if not l.startswith("[morphocuda]")]
     lines = [simplify_errors(l) for l in lines]
     lines = [re.sub(r".*at line.*", STK, l.rstrip()) for l in lines]
     for i in range(len(lines) - 1):
@@ -52,19 +54,39 @@ def main():
     ap.add_argument("--dirs", nargs="*", default=["functionals", "integrate", "mesh", "field", "selection", "sparse", "matrix"])
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--prepend", default=None, help="line put in front of every script, e.g. 'import morphocuda'")
+    ap.add_argument("--jobs", type=int, default=1, help="scripts run concurrently")
     a = ap.parse_args()
     exe = os.path.join(REFOUT, "morpho6")
     env = dict(os.environ, HOME=os.path.join(REFOUT, "home"), OPENBLAS_NUM_THREADS="1")
-    res = {}
+    files = []
     for d in a.dirs:
         for f in sorted(glob.glob(os.path.join(a.root, d, "**", "*.morpho"), recursive=True)):
-            cmd = [exe] + ([f"-w{a.threads}"] if a.threads else []) + [os.path.basename(f)]
-            try:
-                p = subprocess.run(cmd, cwd=os.path.dirname(f), env=env, capture_output=True, text=True, timeout=120)
-                ok = expected_of(f) == output_of(p.stdout + p.stderr)
-            except subprocess.TimeoutExpired:
-                ok = False
-            res[os.path.relpath(f, a.root)] = ok
+            if not os.path.basename(f).startswith("_with_prepend_"):
+                files.append(f)
+
+    def one(f):
+        run = f
+        if a.prepend:
+            # same directory (the scripts open their fixtures by relative path); the extra first line shifts
+            # nothing the expectations depend on (line numbers in stack traces are filtered out)
+            run = os.path.join(os.path.dirname(f), "_with_prepend_" + os.path.basename(f))
+            with open(run, "w", encoding="utf8") as fh:
+                fh.write(a.prepend + "\n" + open(f, encoding="utf8").read())
+        cmd = [exe] + ([f"-w{a.threads}"] if a.threads else []) + [os.path.basename(run)]
+        try:
+            p = subprocess.run(cmd, cwd=os.path.dirname(f), env=env, capture_output=True, text=True, timeout=300)
+            ok = expected_of(f) == output_of(p.stdout + p.stderr)
+        except subprocess.TimeoutExpired:
+            ok = False
+        finally:
+            if run != f and os.path.exists(run):
+                os.remove(run)
+        return os.path.relpath(f, a.root), ok
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(a.jobs, 1)) as ex:
+        res = dict(ex.map(one, files))
     npass = sum(res.values())
     print(f"{npass}/{len(res)} reference tests pass on oracle/_ref")
     for k, v in res.items():

@@ -84,3 +84,44 @@ def test_paranoid_mode_matches_hooked_mode(tmp_path):
     a, _ = run(src, tmp_path, "a.morpho")
     b, _ = run(src, tmp_path, "b.morpho", {"MORPHO_CUDA_PARANOID": "1"})
     assert a == b
+
+
+def _run_reference_suite(prepend, dirs):
+    import json
+    import sys
+    import tempfile
+    out = tempfile.NamedTemporaryFile(suffix=".json", delete=False).name
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "refbuild", "run_ref_tests.py"), "--root", os.path.join(REF, "reftests"),
+           "--dirs", *dirs, "--json", out, "--jobs", str(min(8, os.cpu_count() or 1))]
+    if prepend:
+        cmd += ["--prepend", prepend]
+    subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=3000)
+    return json.load(open(out))
+
+
+REFTESTS = os.path.join(REF, "reftests", "functionals")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFTESTS), reason="oracle/_ref/reftests not built")
+def test_reference_suite_with_inert_extension():
+    """CPU: the reference's own golden-output tests of the hot path still pass with `import morphocuda` in front
+    (no GPU here: the extension loads and patches nothing)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = _run_reference_suite("import morphocuda", ["functionals"])
+    assert r["failed"] == [] and r["total"] >= 100, r
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(REFTESTS), reason="oracle/_ref/reftests not built")
+def test_reference_suite_passes_through_the_extension():
+    """GPU: the reference's OWN test scripts (test/functionals, test/selection, test/field, test/mesh: golden outputs in
+    `// expect:` comments, copied into oracle/_ref/reftests by build_ref.sh; the selection / field / mesh directories
+    pass too: run_ref_tests.py --dirs functionals selection field mesh --prepend "import morphocuda") run with
+    `import morphocuda` prepended —
+    Length/Area/VolumeEnclosed/Volume/AreaEnclosed/LineCurvatureSq/GradSq/NormSq/Nematic/NematicElectric evaluate on the
+    device, everything else on the reference builtins.  Every script that passes on the stock build must pass."""
+    ext = _run_reference_suite("import morphocuda", ["functionals"])       # 107 scripts, a CUDA context each
+    assert ext["total"] >= 100
+    assert ext["failed"] == [], ext["failed"]      # all of them pass on the stock build (oracle/refbuild/REF_TESTS.json)
