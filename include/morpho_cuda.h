@@ -146,6 +146,23 @@ int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, in
 /* number of doubles `mode` produces for this functional on this mesh */
 long mcu_result_size(mcu_mesh *m, const mcu_functional *f, int mode);
 
+/* ---- Line / area integrals of an integrand over the elements: integrate_integrate (integrate.c:769-800), the default
+ *      element integrator behind LineIntegral / AreaIntegral (functional.c:5176-5245, 5354-5428): adaptive Gauss-Kronrod
+ *      7/15 on lines, nested Grundmann-Moeller rules with quadrisection on triangles, accuracy goal 1e-6 relative to the
+ *      element's estimate, result multiplied by the element size.  The reference calls a Morpho closure at every node;
+ *      here the integrand is a postfix program over the interpolated position (MCU_X_POS a = 0,1,2) and the
+ *      interpolated components of the given P1 fields (MCU_X_FIELD a = flattened component index, fields in
+ *      argument order).  mode MCU_TOTAL (1 double) or MCU_INTEGRAND (nel doubles, zero for unselected elements). ---- */
+enum {
+    MCU_X_CONST = 0, MCU_X_POS = 1, MCU_X_FIELD = 2,
+    MCU_X_ADD = 3, MCU_X_SUB = 4, MCU_X_MUL = 5, MCU_X_DIV = 6,
+    MCU_X_NEG = 7, MCU_X_POWI = 8 /* integer power a */, MCU_X_SQRT = 9, MCU_X_SIN = 10, MCU_X_COS = 11, MCU_X_EXP = 12,
+    MCU_X_LOG = 13, MCU_X_ABS = 14
+};
+typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
+int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                 mcu_selection *sel, int mode, double *host_out);
+
 /* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.
  *      kind 0: Coulomb f=1/r, f'=-1/r^2 (examples/thomson/thomson.morpho:26).
  *      mode MCU_TOTAL / MCU_INTEGRAND (n doubles) / MCU_GRADIENT (n*dim doubles). ---- */

@@ -344,7 +344,7 @@ int mcu_selection_get_ids(mcu_selection *s, int *out, int cap) {
     return n;
 }
 
-static int ensure_selection(mcu_selection *s) {
+int mcu_ensure_selection(mcu_selection *s) {
     mcu_mesh *m = s->m;
     if (s->d_eids && s->conn_version == m->conn_version) return MCU_OK;
     selection_release(s);
@@ -477,7 +477,7 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
             mcu_set_error("selection grade %d does not match functional grade %d", sel->g, g);
             return MCU_ERR_ARGS;
         }
-        int rc = ensure_selection(sel);
+        int rc = mcu_ensure_selection(sel);
         if (rc) return rc;
         v.eids = sel->d_eids; v.n = (int) sel->ids.size();
         v.tptr = sel->d_tptr; v.tidx = sel->d_tidx; v.selmask = sel->d_mask;

@@ -1,0 +1,324 @@
+// mcu_integral.cu — quadrature of an integrand over line and area elements on the device.
+//
+// What it replaces: integrate_integrate (src/geometry/integrate.c:769-800), the reference's default ("old")
+// element integrator behind LineIntegral / AreaIntegral (lineintegral_integrand functional.c:5176-5245,
+// areaintegral_integrand 5354-5428): integrate the integrand over the element in barycentric coordinates with an
+// adaptive nested rule, then multiply by the element size.
+//   lines      Gauss 7 / Kronrod 15 pair (integrate.c:38-196): accept when |K15 - G7| * 2^-depth / |global estimate|
+//              < 1e-6, else bisect and average the halves;
+//   triangles  Grundmann-Moeller rules of degree 3, 5, 7 on 4 / 10 / 20 nested points (integrate.c:205-415, "Walkington"):
+//              accept the degree-5 value when it agrees with degree 3, else the degree-7 value when it agrees with
+//              degree 5, else split into four and average.
+// In the reference the integrand is a Morpho closure called through the VM at every node.  A closure cannot
+// run on the device; here the integrand is a small postfix PROGRAM (mcu_expr_op, include/morpho_cuda.h) over the
+// interpolated position and the interpolated components of P1 fields — what a closure→device translator
+// would emit, and what morpho_b200/functionals.py produces by tracing a Python callable.
+//
+// The rule constants are generated, not tabulated: Gauss-Kronrod nodes/weights are the classical 15-point values,
+// the simplex rules come from the Grundmann-Moeller formula  w_i = (-1)^i 2^-2s (d+n-2i)^d / (i! (d+n-i)!),
+// nodes (2 beta + 1)/(d+n-2i), |beta| = s-i  (d = 2s+1, n = 2).
+// The recursion is unrolled into a depth-first walk with an explicit stack; sub-elements are addressed in the
+// barycentric coordinates of the root element, so a leaf contributes  value * (1/2 or 1/4)^depth  — the same number
+// the reference's nested averages produce, up to the association of the sums (1e-16).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mcu_host.h"
+
+extern long g_mcu_launches;
+
+#define MI_MAXQ 16        // interpolated field components
+#define MI_MAXOPS 256
+#define MI_STACK 24       // expression stack
+#define MI_MAXDEPTH_LINE 30
+#define MI_MAXDEPTH_TRI 10
+#define MI_GOAL 1e-6      // INTEGRATE_ACCURACYGOAL (integrate.h:22)
+
+struct MiRules {
+    double gk_t[15], gk_wg[15], gk_wk[15];     // line nodes in [0,1] and the two weight sets (Gauss weights 0 beyond 7)
+    double tri[20][3];                         // triangle nodes (barycentric)
+    double w1[2], w2[3], w3[4];                // weights per group: centroid, degree-3 ring, degree-5 ring, degree-7 ring
+};
+__constant__ MiRules c_rules;
+__constant__ mcu_expr_op c_prog[MI_MAXOPS];
+
+struct MiView {
+    int dim, g, nops, nq, nel;
+    const double *vert;
+    const int *rix;
+    const int *eids;                           // selection or nullptr
+    int n;                                     // elements to visit
+    const double *fld[MI_MAXQ];                // per flattened component: field base pointer
+    int fstride[MI_MAXQ], fcomp[MI_MAXQ];      // psize of that field, component inside an entry
+};
+
+__device__ __forceinline__ double mi_eval(const MiView &v, const double *x, const double *q) {
+    double st[MI_STACK];
+    int sp = 0;
+    for (int i = 0; i < v.nops; i++) {
+        const mcu_expr_op op = c_prog[i];
+        switch (op.op) {
+            case MCU_X_CONST: st[sp++] = op.c; break;
+            case MCU_X_POS: st[sp++] = x[op.a]; break;
+            case MCU_X_FIELD: st[sp++] = q[op.a]; break;
+            case MCU_X_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+            case MCU_X_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+            case MCU_X_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+            case MCU_X_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+            case MCU_X_NEG: st[sp - 1] = -st[sp - 1]; break;
+            case MCU_X_POWI: st[sp - 1] = pow(st[sp - 1], (double) op.a); break;
+            case MCU_X_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+            case MCU_X_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+            case MCU_X_COS: st[sp - 1] = cos(st[sp - 1]); break;
+            case MCU_X_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+            case MCU_X_LOG: st[sp - 1] = log(st[sp - 1]); break;
+            case MCU_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+            default: break;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+// integrand at the point with barycentric coordinates lam[0..nv) of the ROOT element
+template <int NV>
+__device__ __forceinline__ double mi_at(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ], const double *lam) {
+    double x[3] = {0.0, 0.0, 0.0}, q[MI_MAXQ];
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) x[j] += lam[k] * xv[k][j];          // integrate_interpolateposition*
+    for (int i = 0; i < v.nq; i++) {
+        double s = lam[0] * qv[0][i];
+#pragma unroll
+        for (int k = 1; k < NV; k++) s += lam[k] * qv[k][i];            // integrate_interpolatequantities*
+        q[i] = s;
+    }
+    return mi_eval(v, x, q);
+}
+
+__device__ double mi_line(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
+    unsigned stack_idx[MI_MAXDEPTH_LINE + 2];
+    int stack_d[MI_MAXDEPTH_LINE + 2];
+    int top = 0;
+    stack_idx[0] = 0; stack_d[0] = 0; top = 1;
+    double sum = 0.0, gest = 0.0;
+    while (top > 0) {
+        top--;
+        const int d = stack_d[top];
+        const unsigned idx = stack_idx[top];
+        const double w = ldexp(1.0, -d), tlo = (double) idx * w;
+        double r1 = 0.0, r2 = 0.0;
+        for (int i = 0; i < 15; i++) {
+            const double t = tlo + c_rules.gk_t[i] * w;
+            const double lam[2] = {1.0 - t, t};
+            const double f = mi_at<2>(v, xv, qv, lam);
+            if (i < 7) r1 += f * c_rules.gk_wg[i];
+            r2 += f * c_rules.gk_wk[i];
+        }
+        r1 *= 0.5; r2 *= 0.5;
+        if (d == 0) gest = fabs(r2);
+        double eps = (r2 - r1) * w;
+        if (gest > MCU_EPS) eps /= gest;
+        if (fabs(eps) < MI_GOAL || d >= MI_MAXDEPTH_LINE) sum += r2 * w;
+        else {
+            stack_d[top] = d + 1; stack_idx[top] = 2 * idx + 1; top++;     // right half (visited second)
+            stack_d[top] = d + 1; stack_idx[top] = 2 * idx; top++;         // left half
+        }
+    }
+    return sum;
+}
+
+__device__ double mi_tri(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
+    // a sub-triangle = three corners in the barycentric coordinates of the root
+    double sb[3 * MI_MAXDEPTH_TRI + 4][9];
+    int sd[3 * MI_MAXDEPTH_TRI + 4];
+    int top = 0;
+    for (int i = 0; i < 9; i++) sb[0][i] = (i % 4 == 0) ? 1.0 : 0.0;
+    sd[0] = 0; top = 1;
+    double sum = 0.0, gest = 0.0;
+    while (top > 0) {
+        top--;
+        const int d = sd[top];
+        double B[9];
+        for (int i = 0; i < 9; i++) B[i] = sb[top][i];
+        const double af = ldexp(1.0, -2 * d);
+        double r[20];
+        auto node = [&](int i) {
+            double lam[3];
+            for (int k = 0; k < 3; k++) lam[k] = c_rules.tri[i][0] * B[k] + c_rules.tri[i][1] * B[3 + k] + c_rules.tri[i][2] * B[6 + k];
+            return mi_at<3>(v, xv, qv, lam);
+        };
+        for (int i = 0; i < 10; i++) r[i] = node(i);
+        const double rr = r[1] + r[2] + r[3];
+        const double rr2 = r[4] + r[5] + r[6] + r[7] + r[8] + r[9];
+        const double r1 = c_rules.w1[0] * r[0] + c_rules.w1[1] * rr;
+        const double r2 = c_rules.w2[0] * r[0] + c_rules.w2[1] * rr + c_rules.w2[2] * rr2;
+        if (d == 0) gest = fabs(r2);
+        double eps = (r2 - r1) * af;
+        if (gest > MCU_EPS) eps /= gest;
+        if (fabs(eps) < MI_GOAL) { sum += 2.0 * r2 * af; continue; }
+        for (int i = 10; i < 20; i++) r[i] = node(i);
+        double rr3 = 0.0;
+        for (int i = 10; i < 20; i++) rr3 += r[i];
+        const double r3 = c_rules.w3[0] * r[0] + c_rules.w3[1] * rr + c_rules.w3[2] * rr2 + c_rules.w3[3] * rr3;
+        if (d == 0) gest = fabs(2.0 * r3);
+        eps = (r2 - r3) * af;
+        if (gest > MCU_EPS) eps /= gest;
+        if (fabs(eps) < MI_GOAL || d >= MI_MAXDEPTH_TRI) { sum += 2.0 * r3 * af; continue; }
+        // quadrisect: (0, 01, 20) (01, 1, 12) (20, 12, 2) (01, 12, 20); pushed in reverse so they are visited in this order
+        double m01[3], m12[3], m20[3];
+        for (int k = 0; k < 3; k++) { m01[k] = 0.5 * (B[k] + B[3 + k]); m12[k] = 0.5 * (B[3 + k] + B[6 + k]); m20[k] = 0.5 * (B[6 + k] + B[k]); }
+        const double *kids[4][3] = {{B, m01, m20}, {m01, B + 3, m12}, {m20, m12, B + 6}, {m01, m12, m20}};
+        for (int c = 3; c >= 0; c--) {
+            for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) sb[top][3 * j + k] = kids[c][j][k];
+            sd[top] = d + 1; top++;
+        }
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(128) k_integral(MiView v, double *out) {
+    int ce = blockIdx.x * 128 + threadIdx.x;
+    if (ce >= v.n) return;
+    const int e = v.eids ? v.eids[ce] : ce;
+    const int nv = v.g + 1;
+    double xv[3][3], qv[3][MI_MAXQ];
+    for (int k = 0; k < nv; k++) {
+        const int id = v.rix[(size_t) e * nv + k];
+        for (int j = 0; j < 3; j++) xv[k][j] = (j < v.dim) ? v.vert[(size_t) id * v.dim + j] : 0.0;
+        for (int i = 0; i < v.nq; i++) qv[k][i] = v.fld[i][(size_t) id * v.fstride[i] + v.fcomp[i]];
+    }
+    double val, size;
+    if (v.g == 1) {
+        val = mi_line(v, xv, qv);
+        double s[3] = {xv[1][0] - xv[0][0], xv[1][1] - xv[0][1], xv[1][2] - xv[0][2]};
+        size = sqrt(dot3(s, s));
+    } else {
+        val = mi_tri(v, xv, qv);
+        size = area_of(xv);
+    }
+    out[e] = val * size;                               // "*out *= elref.elementsize" (functional.c:5227, 5410)
+}
+
+static __global__ void __launch_bounds__(256) k_isum(const double *__restrict__ v, int n, CompSum *partials) {
+    CompSum acc = {0.0, 0.0};
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) comp_add(acc, v[i]);
+    CompSum r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+static __global__ void __launch_bounds__(256) k_isum_finish(const CompSum *partials, int n, double *out) {
+    CompSum acc = {0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += 256) comp_merge(acc, partials[i]);
+    CompSum r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) out[0] = r.s + r.c;
+}
+
+static void make_rules(MiRules &R) {
+    // Gauss-Kronrod 7/15 on [-1,1]: (node, Gauss weight, Kronrod weight); the Gauss nodes first (their order fixes
+    // only the order of the sums)
+    const double xg[4] = {0.949107912342758524526189684047851, 0.741531185599394439863864773280788,
+                          0.405845151377397166906606412076961, 0.0};
+    const double wg[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+                          0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+    const double wkg[4] = {0.063092092629978553290700663189204, 0.140653259715525918745189590510238,
+                           0.190350578064785409913256402421014, 0.209482141084727828012999174891714};
+    const double xk[4] = {0.991455371120812639206854697526329, 0.864864423359769072789712788640926,
+                          0.586087235467691130294144838258730, 0.207784955007898467600689403773245};
+    const double wk[4] = {0.022935322010529224963732008058970, 0.104790010322250183839876322541518,
+                          0.169004726639267902826583426598550, 0.204432940075298892414161999234649};
+    int n = 0;
+    auto put = [&](double x, double g, double k) { R.gk_t[n] = 0.5 * (1.0 + x); R.gk_wg[n] = g; R.gk_wk[n] = k; n++; };
+    for (int i = 0; i < 3; i++) { put(-xg[i], wg[i], wkg[i]); put(xg[i], wg[i], wkg[i]); }
+    put(0.0, wg[3], wkg[3]);
+    for (int i = 0; i < 4; i++) { put(-xk[i], 0.0, wk[i]); put(xk[i], 0.0, wk[i]); }
+    // Grundmann-Moeller on the triangle (n = 2), s = 1, 2, 3
+    auto fact = [](int k) { double f = 1.0; for (int i = 2; i <= k; i++) f *= i; return f; };
+    auto gmw = [&](int s, int i) {
+        int d = 2 * s + 1;
+        return ((i & 1) ? -1.0 : 1.0) * std::ldexp(1.0, -2 * s) * std::pow((double) (d + 2 - 2 * i), d) / (fact(i) * fact(d + 2 - i));
+    };
+    // the formula's weights sum to 1/2 (the area of the reference triangle); the integrators double the weighted sum
+    for (int s = 1; s <= 3; s++) {
+        double *w = (s == 1) ? R.w1 : (s == 2 ? R.w2 : R.w3);
+        for (int i = 0; i <= s; i++) w[s - i] = gmw(s, i);      // group index: 0 = centroid (i = s), 1 = denominators 5, ...
+    }
+    // nodes: centroid; (3,1,1)/5; (5,1,1)/7 and (3,3,1)/7; (7,1,1)/9, (5,3,1)/9 and (3,3,3)/9
+    int p = 0;
+    auto node = [&](double a, double b, double c, double den) { R.tri[p][0] = a / den; R.tri[p][1] = b / den; R.tri[p][2] = c / den; p++; };
+    node(1, 1, 1, 3);
+    node(3, 1, 1, 5); node(1, 3, 1, 5); node(1, 1, 3, 5);
+    node(5, 1, 1, 7); node(1, 5, 1, 7); node(1, 1, 5, 7); node(3, 3, 1, 7); node(3, 1, 3, 7); node(1, 3, 3, 7);
+    node(7, 1, 1, 9); node(1, 7, 1, 9); node(1, 1, 7, 9);
+    node(3, 5, 1, 9); node(3, 1, 5, 9); node(5, 3, 1, 9); node(5, 1, 3, 9); node(1, 3, 5, 9); node(1, 5, 3, 9);
+    node(3, 3, 3, 9);
+}
+
+extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                            mcu_selection *sel, int mode, double *host_out) {
+    if (!m || (grade != 1 && grade != 2) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0 || !host_out ||
+        (mode != MCU_TOTAL && mode != MCU_INTEGRAND)) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
+    if (!m->conn[grade].present) { mcu_set_error("mesh has no elements of grade %d", grade); return MCU_ERR_ELNOTFOUND; }
+    if (sel && (sel->m != m || sel->g != grade)) { mcu_set_error("selection does not belong to this mesh / grade"); return MCU_ERR_ARGS; }
+    static bool rules_up = false;
+    cudaStream_t st = mcu_stream();
+    if (!rules_up) {
+        MiRules R;
+        make_rules(R);
+        if (cudaMemcpyToSymbol(c_rules, &R, sizeof(R)) != cudaSuccess) { mcu_set_error("rule upload failed"); return MCU_ERR_CUDA; }
+        rules_up = true;
+    }
+    MiView v;
+    memset(&v, 0, sizeof(v));
+    v.dim = m->dim; v.g = grade; v.nops = nops; v.nel = m->conn[grade].nel;
+    v.vert = m->d_vert; v.rix = m->conn[grade].d_rix;
+    if (sel) { int rs = mcu_ensure_selection(sel); if (rs) return rs; }
+    v.eids = sel ? sel->d_eids : nullptr;
+    v.n = sel ? (int) sel->ids.size() : v.nel;
+    for (int f = 0; f < nfields; f++) {
+        if (!fields[f] || fields[f]->m != m) { mcu_set_error("field does not belong to this mesh"); return MCU_ERR_ARGS; }
+        for (int c = 0; c < fields[f]->psize; c++) {
+            if (v.nq == MI_MAXQ) { mcu_set_error("too many field components (max %d)", MI_MAXQ); return MCU_ERR_UNSUPPORTED; }
+            v.fld[v.nq] = fields[f]->d_data; v.fstride[v.nq] = fields[f]->psize; v.fcomp[v.nq] = c; v.nq++;
+        }
+    }
+    // validate the program: stack discipline and operand ranges
+    int depth = 0;
+    for (int i = 0; i < nops; i++) {
+        const mcu_expr_op &op = prog[i];
+        if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
+            if ((op.op == MCU_X_POS && (op.a < 0 || op.a > 2)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= v.nq))) { mcu_set_error("integrand operand out of range at op %d", i); return MCU_ERR_ARGS; }
+            depth++;
+        } else if (op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) { if (depth < 2) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
+        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_ABS) { if (depth < 1) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        else { mcu_set_error("unknown integrand op %d", op.op); return MCU_ERR_ARGS; }
+        if (depth > MI_STACK) { mcu_set_error("integrand stack too deep"); return MCU_ERR_UNSUPPORTED; }
+    }
+    if (depth != 1) { mcu_set_error("integrand program leaves %d values", depth); return MCU_ERR_ARGS; }
+    if (cudaMemcpyToSymbolAsync(c_prog, prog, sizeof(mcu_expr_op) * nops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return MCU_ERR_CUDA;
+    double *d_int = nullptr, *d_tot = nullptr;
+    CompSum *d_part = nullptr;
+    int rc = MCU_OK;
+    const int nel = v.nel;
+    if (cudaMalloc((void **) &d_int, sizeof(double) * std::max(nel, 1)) != cudaSuccess) return MCU_ERR_ALLOC;
+    cudaMemsetAsync(d_int, 0, sizeof(double) * std::max(nel, 1), st);
+    if (v.n > 0) { k_integral<<<(v.n + 127) / 128, 128, 0, st>>>(v, d_int); g_mcu_launches += 1; }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mode == MCU_TOTAL) {
+        int rb = std::max(1, std::min(1024, (nel + 255) / 256));
+        if (cudaMalloc((void **) &d_part, sizeof(CompSum) * rb) != cudaSuccess || cudaMalloc((void **) &d_tot, 8) != cudaSuccess) rc = MCU_ERR_ALLOC;
+        else {
+            k_isum<<<rb, 256, 0, st>>>(d_int, nel, d_part);
+            k_isum_finish<<<1, 256, 0, st>>>(d_part, rb, d_tot);
+            g_mcu_launches += 2;
+            e = cudaMemcpyAsync(host_out, d_tot, 8, cudaMemcpyDeviceToHost, st);
+        }
+    } else if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_int, sizeof(double) * nel, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { mcu_set_error("integral failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
+    cudaFree(d_int);
+    if (d_part) cudaFree(d_part);
+    if (d_tot) cudaFree(d_tot);
+    return rc;
+}

@@ -20,7 +20,7 @@ from ._lib import (MCU_FIELDGRADIENT, MCU_GRADIENT, MCU_INTEGRAND, MCU_TOTAL, FU
 from .geometry import Field, Mesh, Selection
 
 __all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq",
-           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential"]
+           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral"]
 
 
 class Functional:
@@ -212,3 +212,49 @@ class PairwisePotential:
 
     def gradient(self, mesh):
         return self._run(mesh, MCU_GRADIENT, mesh.nv * mesh.dim).reshape(mesh.nv, mesh.dim)
+
+
+class _Integral:
+    """LineIntegral / AreaIntegral (functional.c:5186-5243, 5371-5426): the integral over every element of a callable
+    of the position and of the interpolated field values, by the reference's default adaptive quadrature
+    (integrate_integrate, integrate.c:769-800; mcu_integral.cu on the device).  ``fn(x, *q)`` is written with the
+    operators and functions of :mod:`morpho_b200.integrand`; it is recorded once into a postfix program.  Only
+    ``total`` and ``integrand`` exist on the device path (the reference's gradients re-enter the VM per FD probe)."""
+    grade = 0
+
+    def __init__(self, fn, *fields):
+        self.fn = fn
+        self.fields = list(fields)
+        self._prog = None
+
+    def program(self, dim):
+        if self._prog is None or self._prog[0] != dim:
+            from .integrand import trace
+            self._prog = (dim, trace(self.fn, dim, [f.psize for f in self.fields]))
+        return self._prog[1]
+
+    def _eval(self, mode, args):
+        mesh, sel, _ = Functional._args(args)
+        prog = self.program(mesh.dim)
+        nel = mesh.count(self.grade)
+        if nel == 0 and self.grade not in mesh._conn:
+            raise MorphoError(_lib.MCU_ERR_ELNOTFOUND, "FnctlELNtFnd", f"Mesh does not provide elements of grade {self.grade}.")
+        out = np.zeros(max(nel, 1) if mode == MCU_INTEGRAND else 1, dtype=np.float64)
+        fh = (C.c_void_p * max(len(self.fields), 1))(*[f._h for f in self.fields])
+        hsel = sel._handle(self.grade) if sel is not None else None
+        check(lib().mcu_integral(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, mode, out.ctypes.data))
+        return out[:nel] if mode == MCU_INTEGRAND else out
+
+    def total(self, *args):
+        return float(self._eval(MCU_TOTAL, args)[0])
+
+    def integrand(self, *args):
+        return self._eval(MCU_INTEGRAND, args)
+
+
+class LineIntegral(_Integral):
+    grade = 1
+
+
+class AreaIntegral(_Integral):
+    grade = 2

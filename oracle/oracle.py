@@ -240,6 +240,8 @@ class Reference:
                                 C.POINTER(C.c_double), C.c_long, C.POINTER(C.c_double)]
         L.refh_time.restype = C.c_double
         L.refh_time.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.refh_integral.restype = C.c_long
+        L.refh_integral.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refh_fdstepsize.restype = C.c_double
         L.refh_fdstepsize.argtypes = [C.c_double, C.c_int]
         rc = L.refh_init(int(nthreads))
@@ -282,6 +284,29 @@ class RefMesh:
 
     def addgrade(self, g):
         return self.ref.lib.refh_mesh_addgrade(self.h, g)
+
+    def integral(self, g, prog, fields=()):
+        """Per-element integrals through the reference's OWN integrate_integrate (integrate.c:769-800) with the postfix
+        program ``prog`` (list of (op, a, c), include/morpho_cuda.h) as the integrand; ``fields`` are (nv, psize) arrays
+        whose components are the interpolated quantities, flattened in order."""
+        ops = np.zeros(len(prog), dtype=np.dtype([("op", "<i4"), ("a", "<i4"), ("c", "<f8")]))
+        for i, (op, a, c) in enumerate(prog):
+            ops[i] = (op, a, c)
+        comps, keep = [], []
+        for f in fields:
+            f = np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(self.nv, -1))
+            keep.append(f)
+            for k in range(f.shape[1]):
+                comps.append((f.ctypes.data + 8 * k, f.shape[1]))
+        nq = len(comps)
+        ptrs = (C.c_void_p * max(nq, 1))(*[p for p, _ in comps])
+        strides = np.array([s for _, s in comps] or [1], dtype=np.int32)
+        nel = self.count(g)
+        out = np.zeros(max(nel, 1), dtype=np.float64)
+        n = self.ref.lib.refh_integral(self.h, g, len(prog), ops.ctypes.data, nq, ptrs, strides.ctypes.data, out.ctypes.data)
+        if n < 0:
+            raise RuntimeError("refh_integral failed: " + self.ref.err())
+        return out[:n]
 
     def count(self, g):
         return self.ref.lib.refh_mesh_grade_count(self.h, g)

@@ -37,6 +37,7 @@
 #include "field.h"
 #include "selection.h"
 #include "functional.h"
+#include "integrate.h"
 
 static vm *hvm = NULL;
 static program *hprog = NULL;
@@ -328,3 +329,73 @@ double refh_time(void *func, const char *method, void *mesh, void *sel, void *fi
  * function of the library but has no prototype in functional.h */
 double functional_fdstepsize(double x, int order);
 double refh_fdstepsize(double x, int order) { return functional_fdstepsize(x, order); }
+
+
+/* ---------------- Quadrature: the reference's own element integrator with a C integrand ----------------
+ * integrate_integrate (integrate.c:769-800) is what LineIntegral / AreaIntegral call when no method dictionary is
+ * given (functional.c:5223, 5406), with a callback that re-enters the VM for a Morpho closure.  Here the callback
+ * interprets the same postfix program the CUDA library runs (include/morpho_cuda.h, mcu_expr_op): the quadrature
+ * is the reference's, the integrand is ours.  Result per element = integral * element size (functional.c:5227). */
+typedef struct { int op; int a; double c; } refh_expr_op;
+typedef struct { int nops; const refh_expr_op *prog; } refh_prog;
+
+static bool refh_integrand(unsigned int dim, double *lambda, double *x, unsigned int nq, value *q, void *ref, double *fout) {
+    const refh_prog *pr = (const refh_prog *) ref;
+    double st[64], xx[3] = {0, 0, 0};
+    int sp = 0;
+    for (unsigned int k = 0; k < dim && k < 3; k++) xx[k] = x[k];
+    (void) lambda;
+    for (int i = 0; i < pr->nops; i++) {
+        const refh_expr_op *op = &pr->prog[i];
+        switch (op->op) {
+            case 0: st[sp++] = op->c; break;
+            case 1: st[sp++] = xx[op->a]; break;
+            case 2: { double v = 0.0; if ((unsigned) op->a < nq) morpho_valuetofloat(q[op->a], &v); st[sp++] = v; break; }
+            case 3: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+            case 4: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+            case 5: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+            case 6: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+            case 7: st[sp - 1] = -st[sp - 1]; break;
+            case 8: st[sp - 1] = pow(st[sp - 1], (double) op->a); break;
+            case 9: st[sp - 1] = sqrt(st[sp - 1]); break;
+            case 10: st[sp - 1] = sin(st[sp - 1]); break;
+            case 11: st[sp - 1] = cos(st[sp - 1]); break;
+            case 12: st[sp - 1] = exp(st[sp - 1]); break;
+            case 13: st[sp - 1] = log(st[sp - 1]); break;
+            case 14: st[sp - 1] = fabs(st[sp - 1]); break;
+            default: return false;
+        }
+    }
+    *fout = st[sp - 1];
+    return true;
+}
+
+/* out[e] = integral over element e of grade g (all elements); fields: nq flattened components, comp[i] points at the
+ * nv-long array of component i at the vertices (stride given).  Returns the number of elements or -1. */
+long refh_integral(void *mesh, int g, int nops, const refh_expr_op *prog, int nq, const double **comp, const int *stride, double *out) {
+    objectmesh *m = (objectmesh *) mesh;
+    objectsparse *s = mesh_getconnectivityelement(m, 0, (unsigned) g);
+    if (!s || nq > 32) return -1;
+    refh_prog pr = {nops, prog};
+    int nel = s->ccs.ncols;
+    for (int e = 0; e < nel; e++) {
+        int nv, *vid;
+        if (!sparseccs_getrowindices(&s->ccs, e, &nv, &vid) || nv != g + 1) return -1;
+        double *x[4];
+        value qv[4][33];
+        value *q[4];
+        for (int k = 0; k < nv; k++) {
+            x[k] = m->vert->elements + (size_t) vid[k] * m->vert->nrows;
+            for (int i = 0; i < nq; i++) qv[k][i] = MORPHO_FLOAT(comp[i][(size_t) vid[k] * stride[i]]);
+            q[k] = qv[k];
+        }
+        double size, val;
+        if (!functional_elementsize(hvm, m, g, e, nv, vid, &size)) return -1;
+        if (!integrate_integrate(refh_integrand, m->dim, (unsigned) g, x, (unsigned) nq, nq ? q : NULL, &pr, &val)) {
+            snprintf(lasterr, sizeof(lasterr), "integrate_integrate failed on element %d", e);
+            return -1;
+        }
+        out[e] = val * size;
+    }
+    return nel;
+}

@@ -1,0 +1,55 @@
+"""Seeded cases for LineIntegral / AreaIntegral: each integrand is written twice, as a Python callable for the
+device path (recorded by morpho_b200.integrand.trace) and as the Morpho closure the unmodified VM runs when the
+golden file is made.  Fields are polynomials of the vertex position so that both sides build the same values."""
+import numpy as np
+
+from morpho_b200 import meshgen as mg
+from morpho_b200.integrand import cos, exp, log, sin, sqrt
+
+
+def _fields(vert):
+    x, y = vert[:, 0], vert[:, 1]
+    z = vert[:, 2] if vert.shape[1] > 2 else np.zeros_like(x)
+    phi = x * x - 0.5 * y + 0.25 * z
+    q = np.stack([x + 0.5 * z, y * y, x * y - z], axis=1)
+    return {"phi": phi.reshape(-1, 1), "q": q}
+
+
+# Morpho source of the same fields (Field(mesh, fn (x,y,z) ...)); 2D meshes get fn (x,y)
+FIELD_SRC = {
+    3: {"phi": "fn (x,y,z) x*x-0.5*y+0.25*z", "q": "fn (x,y,z) Matrix([x+0.5*z, y*y, x*y-z])"},
+    2: {"phi": "fn (x,y) x*x-0.5*y+0.25*0", "q": "fn (x,y) Matrix([x+0.5*0, y*y, x*y-0])"},
+}
+
+
+def meshes():
+    out = {}
+    v, c = mg.icosphere(3)
+    v = mg.perturb_radially(v, 0.02, 5)
+    out["sphere"] = (v, {1: mg.edges_from_faces(c), 2: c})
+    v, c, _ = mg.disk(5, 2)
+    out["disk2d"] = (v, {1: mg.edges_from_faces(c), 2: c})
+    v, e = mg.polyline_loop(24, 3, 11, 0.1)
+    out["loop"] = (v, {1: e})
+    return out
+
+
+# name, mesh, grade, python callable, morpho closure, fields, selection ids or None
+CASES = [
+    ("line_poly", "loop", 1, lambda x: x[0] ** 2 * x[1] + 1.0, "fn (x) x[0]^2*x[1]+1", [], None),
+    ("line_osc", "loop", 1, lambda x: sin(9 * x[0]) * exp(x[1]) + cos(7 * x[2]), "fn (x) sin(9*x[0])*exp(x[1])+cos(7*x[2])", [], None),
+    ("line_sqrt", "sphere", 1, lambda x: sqrt(x[0] ** 2 + 0.01) / (1.5 + x[2]), "fn (x) sqrt(x[0]^2+0.01)/(1.5+x[2])", [], None),
+    ("line_field", "sphere", 1, lambda x, p, q: p * q[1] - q[2] * x[0] + abs(q[0]), "fn (x, p, q) p*q[1]-q[2]*x[0]+abs(q[0])", ["phi", "q"], None),
+    ("line_sel", "loop", 1, lambda x, p: log(2.0 + p * p) * x[1], "fn (x, p) log(2+p*p)*x[1]", ["phi"], [0, 3, 4, 11, 23]),
+    ("line_2d", "disk2d", 1, lambda x: exp(-4 * (x[0] ** 2 + x[1] ** 2)), "fn (x) exp(-4*(x[0]^2+x[1]^2))", [], None),
+    ("area_const", "sphere", 2, lambda x: 1.0 + 0 * x[0], "fn (x) 1+0*x[0]", [], None),
+    ("area_quad", "sphere", 2, lambda x: x[0] * x[1] + x[2] ** 2, "fn (x) x[0]*x[1]+x[2]^2", [], None),
+    ("area_osc", "sphere", 2, lambda x: exp(x[0]) * cos(6 * x[1]) + sin(5 * x[2]) ** 2, "fn (x) exp(x[0])*cos(6*x[1])+sin(5*x[2])^2", [], None),
+    ("area_peak", "disk2d", 2, lambda x: 1.0 / (0.02 + (x[0] - 0.3) ** 2 + x[1] ** 2), "fn (x) 1/(0.02+(x[0]-0.3)^2+x[1]^2)", [], None),
+    ("area_field", "sphere", 2, lambda x, p, q: p * p + q[0] * q[1] - q[2] * x[2], "fn (x, p, q) p*p+q[0]*q[1]-q[2]*x[2]", ["phi", "q"], None),
+    ("area_sel", "sphere", 2, lambda x, q: sqrt(1.0 + q[1]) * exp(-x[2]), "fn (x, q) sqrt(1+q[1])*exp(-x[2])", ["q"], [1, 2, 17, 40, 41, 99, 150]),
+]
+
+
+def fields_for(vert):
+    return _fields(vert)

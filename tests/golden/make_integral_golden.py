@@ -1,0 +1,85 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/integrals.npz from the UNMODIFIED reference, twice:
+
+ (1) through the reference's VM: a generated Morpho script loads each mesh from a .mesh file, builds the fields and
+     prints ``LineIntegral(closure, fields...).integrand(mesh)`` / ``AreaIntegral(...)`` — the real builtin with a real
+     closure (functional.c:5186-5243, 5371-5426);
+ (2) through oracle/refbuild/ref_harness.c's refh_integral: the reference's own integrate_integrate with the
+     bytecode interpreter as the integrand callback.
+
+Both must agree (1e-13 of the element scale) — that pins the bytecode route the GPU tests use as their live
+reference — and (1) is what gets stored.   Run in the dev container:   python tests/golden/make_integral_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+
+from morpho_b200 import meshgen as mg  # noqa: E402
+from morpho_b200.integrand import trace  # noqa: E402
+from oracle.oracle import Reference  # noqa: E402
+from tests.golden.integral_cases import CASES, FIELD_SRC, fields_for, meshes  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def vm_integrands(tmp, ms):
+    src = ["import meshtools", ""]
+    for name, (v, gr) in ms.items():
+        mg.write_mesh_file(os.path.join(tmp, name + ".mesh"), v, **{f"g{g}": c for g, c in gr.items()})
+        src.append(f'var m_{name} = Mesh("{name}.mesh")')
+        for fname, fsrc in FIELD_SRC[v.shape[1]].items():
+            src.append(f"var {fname}_{name} = Field(m_{name}, {fsrc})")
+    for name, mesh, grade, _, closure, flds, sel in CASES:
+        cls = "LineIntegral" if grade == 1 else "AreaIntegral"
+        fargs = "".join(f", {f}_{mesh}" for f in flds)
+        src.append(f"var r_{name} = {cls}({closure}{fargs}).integrand(m_{mesh})")
+        src.append(f'print "@{name}"')
+        src.append(f'for (i in 0...r_{name}.dimensions()[1]) print r_{name}[0,i].format("%.17g")')
+    path = os.path.join(tmp, "integrals.morpho")
+    open(path, "w").write("\n".join(src) + "\n")
+    env = dict(os.environ, HOME=os.path.join(REF, "home"), OPENBLAS_NUM_THREADS="1")
+    p = subprocess.run([os.path.join(REF, "morpho6"), path], capture_output=True, text=True, cwd=tmp, env=env, timeout=600)
+    if p.returncode != 0 or "rror" in p.stdout:
+        raise SystemExit(p.stdout + p.stderr)
+    out, cur = {}, None
+    for line in p.stdout.splitlines():
+        if line.startswith("@"):
+            cur = line[1:]
+            out[cur] = []
+        elif cur and line.strip():
+            out[cur].append(float(line))
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def main():
+    ms = meshes()
+    with tempfile.TemporaryDirectory() as tmp:
+        vm = vm_integrands(tmp, ms)
+    ref = Reference(0)
+    store = {}
+    for name, mesh, grade, fn, _, flds, sel in CASES:
+        v, gr = ms[mesh]
+        fd = fields_for(v)
+        prog = trace(fn, v.shape[1], [fd[f].shape[1] for f in flds])
+        rm = ref.mesh(v, gr)
+        h = rm.integral(grade, [tuple(t) for t in prog.tolist()], [fd[f] for f in flds])
+        rm.free()
+        g = vm[name]
+        assert g.shape == h.shape, (name, g.shape, h.shape)
+        err = np.max(np.abs(g - h)) / max(np.max(np.abs(g)), 1e-300)
+        print(f"{name:12s} n={g.size:5d} sum={g.sum():+.15e}  VM closure vs harness bytecode: {err:.2e}")
+        assert err < 1e-13, name
+        store[name] = g
+    np.savez_compressed(os.path.join(HERE, "integrals.npz"), **store)
+    print("wrote integrals.npz")
+
+
+if __name__ == "__main__":
+    main()

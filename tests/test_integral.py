@@ -1,0 +1,149 @@
+"""LineIntegral / AreaIntegral: the device quadrature (morpho_b200/csrc/mcu_integral.cu) against golden vectors made
+by the unmodified reference running real closures in its VM (tests/golden/make_integral_golden.py), and against the
+reference's own integrate_integrate called live through the harness where oracle/_ref is present.
+
+Tolerance 1e-12 of the largest element value: the subdivision decisions are discrete (error estimate < 1e-6), so a
+device that took a different refinement path anywhere would miss by ~1e-8 or more and fail."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.integral_cases import CASES, fields_for, meshes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "integrals.npz")
+TOL = 1e-12
+
+
+def _prog(fn, dim, flds, fd):
+    from morpho_b200.integrand import trace
+    return trace(fn, dim, [fd[f].shape[1] for f in flds])
+
+
+# ---------------------------------------------------------------- CPU: tracer + the pinned checker
+def test_tracer_programs_are_well_formed():
+    from morpho_b200.integrand import OPS
+    ms = meshes()
+    for name, mesh, grade, fn, _, flds, sel in CASES:
+        v, _ = ms[mesh]
+        prog = _prog(fn, v.shape[1], flds, fields_for(v))
+        depth = 0
+        for op, a, c in prog.tolist():
+            if op in (OPS["const"], OPS["pos"], OPS["field"]):
+                depth += 1
+            elif OPS["add"] <= op <= OPS["div"]:
+                assert depth >= 2, name
+                depth -= 1
+            else:
+                assert depth >= 1, name
+        assert depth == 1, name
+
+
+def test_reference_integrator_reproduces_vm_goldens(reference):
+    gold = np.load(GOLD)
+    ms = meshes()
+    for name, mesh, grade, fn, _, flds, sel in CASES:
+        v, gr = ms[mesh]
+        fd = fields_for(v)
+        prog = _prog(fn, v.shape[1], flds, fd)
+        rm = reference.mesh(v, gr)
+        got = rm.integral(grade, [tuple(t) for t in prog.tolist()], [fd[f] for f in flds])
+        rm.free()
+        np.testing.assert_allclose(got, gold[name], rtol=0, atol=1e-13 * np.max(np.abs(gold[name])), err_msg=name)
+
+
+def test_goldens_against_closed_forms():
+    """Independent of any code of ours: sum over the sphere of the constant integrand is the mesh area, and the
+    polynomial line integrand has a closed form per segment."""
+    gold = np.load(GOLD)
+    ms = meshes()
+    v, gr = ms["sphere"]
+    t = v[gr[2]]
+    area = 0.5 * np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1)
+    np.testing.assert_allclose(gold["area_const"], area, rtol=1e-13)
+    v, gr = ms["loop"]
+    a, b = v[gr[1][:, 0]], v[gr[1][:, 1]]
+    ln = np.linalg.norm(b - a, axis=1)
+    # int_0^1 (x0+t dx)^2 (y0+t dy) dt + 1
+    x0, dx, y0, dy = a[:, 0], b[:, 0] - a[:, 0], a[:, 1], b[:, 1] - a[:, 1]
+    exact = (x0 * x0 * y0 + (2 * x0 * dx * y0 + x0 * x0 * dy) / 2 + (dx * dx * y0 + 2 * x0 * dx * dy) / 3 + dx * dx * dy / 4 + 1) * ln
+    np.testing.assert_allclose(gold["line_poly"], exact, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- GPU: the device quadrature
+@pytest.fixture(scope="module")
+def mb():
+    import morpho_b200 as mb
+    mb.init(0)
+    return mb
+
+
+def _device(mb, case, ms):
+    name, mesh, grade, fn, _, flds, sel = case
+    v, gr = ms[mesh]
+    fd = fields_for(v)
+    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2))
+    fl = [mb.Field(m, fd[f]) for f in flds]
+    cls = mb.LineIntegral if grade == 1 else mb.AreaIntegral
+    args = [m] + ([mb.Selection(m, ids={grade: sel})] if sel is not None else [])
+    func = cls(fn, *fl)
+    return func.integrand(*args), func.total(*args)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_device_quadrature_matches_vm_goldens(mb, case):
+    gold = np.load(GOLD)[case[0]].copy()
+    if case[6] is not None:
+        mask = np.zeros(gold.size, dtype=bool)
+        mask[case[6]] = True
+        gold[~mask] = 0.0                         # unselected elements keep 0 (functional.c:226-229)
+    integrand, total = _device(mb, case, meshes())
+    scale = np.max(np.abs(gold))
+    err = np.max(np.abs(integrand - gold)) / scale
+    print(case[0], f"integrand err {err:.2e}")
+    assert err <= TOL, case[0]
+    s = c = 0.0
+    for y in gold:                                # the reference's serial Kahan sum (functional.c:243-253)
+        yy = y - c
+        tt = s + yy
+        c = (tt - s) - yy
+        s = tt
+    assert abs(total - s) <= TOL * max(abs(s), scale), case[0]
+
+
+@pytest.mark.gpu
+def test_device_quadrature_large_mesh_vs_live_reference(mb, reference):
+    """20k triangles / 30k edges with integrands that need several levels of refinement on part of the mesh."""
+    from morpho_b200 import meshgen as mg
+    from morpho_b200.integrand import cos, exp, sin
+    v, c = mg.icosphere(32)
+    e = mg.edges_from_faces(c)
+    fd = fields_for(v)
+    fn2 = lambda x, q: exp(2 * x[0]) * cos(25 * x[1] * x[2]) + q[0] * q[1]      # noqa: E731
+    fn1 = lambda x, q: sin(40 * x[0] * x[1]) / (1.2 + x[2]) + q[2]               # noqa: E731
+    m = mb.Mesh(v, edges=e, faces=c)
+    q = mb.Field(m, fd["q"])
+    rm = reference.mesh(v, {1: e, 2: c})
+    for grade, fn, cls in ((2, fn2, mb.AreaIntegral), (1, fn1, mb.LineIntegral)):
+        prog = _prog(fn, 3, ["q"], fd)
+        want = rm.integral(grade, [tuple(t) for t in prog.tolist()], [fd["q"]])
+        got = cls(fn, q).integrand(m)
+        err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+        print(f"grade {grade}: n={want.size} err {err:.2e}")
+        assert err <= TOL
+    rm.free()
+
+
+@pytest.mark.gpu
+def test_integral_rejects_bad_programs(mb):
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(2)
+    m = mb.Mesh(v, faces=c)
+    with pytest.raises(mb.MorphoError):
+        mb.LineIntegral(lambda x: x[0]).total(m)          # no edges: FnctlELNtFnd like functional.c:115-129
+    f = mb.AreaIntegral(lambda x: x[0])
+    f._prog = (3, np.zeros(1, dtype=f.program(3).dtype))
+    f._prog[1][0] = (3, 0, 0.0)                           # ADD on an empty stack
+    with pytest.raises(mb.MorphoError):
+        f.total(m)
