@@ -157,7 +157,10 @@ enum {
     MCU_X_CONST = 0, MCU_X_POS = 1, MCU_X_FIELD = 2,
     MCU_X_ADD = 3, MCU_X_SUB = 4, MCU_X_MUL = 5, MCU_X_DIV = 6,
     MCU_X_NEG = 7, MCU_X_POWI = 8 /* integer power a */, MCU_X_SQRT = 9, MCU_X_SIN = 10, MCU_X_COS = 11, MCU_X_EXP = 12,
-    MCU_X_LOG = 13, MCU_X_ABS = 14
+    MCU_X_LOG = 13, MCU_X_ABS = 14,
+    MCU_X_POW = 15 /* binary: pow(l, r) */, MCU_X_TAN = 16, MCU_X_ASIN = 17, MCU_X_ACOS = 18, MCU_X_ATAN = 19,
+    MCU_X_ATAN2 = 20 /* binary: atan2(l, r) */, MCU_X_SINH = 21, MCU_X_COSH = 22, MCU_X_TANH = 23, MCU_X_FLOOR = 24,
+    MCU_X_CEIL = 25, MCU_X_LOG10 = 26
 };
 typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
 int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,

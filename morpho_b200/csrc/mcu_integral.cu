@@ -75,6 +75,18 @@ __device__ __forceinline__ double mi_eval(const MiView &v, const double *x, cons
             case MCU_X_EXP: st[sp - 1] = exp(st[sp - 1]); break;
             case MCU_X_LOG: st[sp - 1] = log(st[sp - 1]); break;
             case MCU_X_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+            case MCU_X_POW: sp--; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+            case MCU_X_ATAN2: sp--; st[sp - 1] = atan2(st[sp - 1], st[sp]); break;
+            case MCU_X_TAN: st[sp - 1] = tan(st[sp - 1]); break;
+            case MCU_X_ASIN: st[sp - 1] = asin(st[sp - 1]); break;
+            case MCU_X_ACOS: st[sp - 1] = acos(st[sp - 1]); break;
+            case MCU_X_ATAN: st[sp - 1] = atan(st[sp - 1]); break;
+            case MCU_X_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
+            case MCU_X_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
+            case MCU_X_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+            case MCU_X_FLOOR: st[sp - 1] = floor(st[sp - 1]); break;
+            case MCU_X_CEIL: st[sp - 1] = ceil(st[sp - 1]); break;
+            case MCU_X_LOG10: st[sp - 1] = log10(st[sp - 1]); break;
             default: break;
         }
     }
@@ -290,8 +302,8 @@ extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op 
         if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
             if ((op.op == MCU_X_POS && (op.a < 0 || op.a > 2)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= v.nq))) { mcu_set_error("integrand operand out of range at op %d", i); return MCU_ERR_ARGS; }
             depth++;
-        } else if (op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) { if (depth < 2) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
-        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_ABS) { if (depth < 1) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2) { if (depth < 2) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
+        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) { if (depth < 1) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } }
         else { mcu_set_error("unknown integrand op %d", op.op); return MCU_ERR_ARGS; }
         if (depth > MI_STACK) { mcu_set_error("integrand stack too deep"); return MCU_ERR_UNSUPPORTED; }
     }

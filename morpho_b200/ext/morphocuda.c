@@ -27,6 +27,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* MORPHO_CORE: the integrand translator reads bytecode and the VM's globals (core.h); the reference's own geometry
+ * sources are compiled the same way */
+#define MORPHO_CORE
+#include "core.h"
 #include "morpho.h"
 #include "builtin.h"
 #include "classes.h"
@@ -38,6 +42,7 @@
 #include "functional.h"
 
 #include "morpho_cuda.h"
+#include "mc_translate.h"
 
 #define MC_MAXMIRRORS 64
 #define MC_MAXWRAPS 48
@@ -393,6 +398,99 @@ MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, total, MCU_TOTAL)
 MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, integrand, MCU_INTEGRAND)
 MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, gradient, MCU_GRADIENT)
 
+/* LineIntegral / AreaIntegral, total and integrand (functional.c:5186-5243, 5371-5426).  The integrand closure is
+ * translated into a postfix program (mc_translate.h); what cannot be translated — and method dictionaries, reference
+ * meshes, fields on finite-element spaces — goes to the reference builtin. */
+#define MC_MAXPROG 256
+static long mc_stat_translated = 0;
+static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, value *out) {
+    functional_mapinfo info;
+    *out = MORPHO_NIL;
+    if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
+    if (!functional_validateargs(v, nargs, args, &info)) return true;
+    objectinstance *self = MORPHO_GETINSTANCE(MORPHO_SELF(args));
+    if (info.field || (info.sel && info.sel->mode != SELECT_SOME) || mesh_has_symmetries(info.mesh, g)) return false;
+    value fn = MORPHO_NIL, val = MORPHO_NIL;
+    if (!prop(self, SCALARPOTENTIAL_FUNCTION_PROPERTY, &fn)) return false;
+    if (prop(self, INTEGRAL_METHOD_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;            /* new integrator */
+    if (prop(self, LINEARELASTICITY_REFERENCE_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;
+    if (prop(self, LINEARELASTICITY_WTBYREF_PROPERTY, &val) && MORPHO_ISTRUE(val)) return false;
+    objectfield *flds[16];
+    int nf = 0, rows[16], cols[16];
+    if (prop(self, FUNCTIONAL_FIELD_PROPERTY, &val) && MORPHO_ISLIST(val)) {
+        objectlist *l = MORPHO_GETLIST(val);
+        if (l->val.count > 16) return false;
+        for (unsigned int i = 0; i < l->val.count; i++) {
+            if (!MORPHO_ISFIELD(l->val.data[i])) return false;
+            objectfield *f = MORPHO_GETFIELD(l->val.data[i]);
+            if (!field_is_vertex_field(f, info.mesh)) return false;
+            if (MORPHO_ISMATRIX(f->prototype)) {
+                objectmatrix *pm = MORPHO_GETMATRIX(f->prototype);
+                if (pm->nvals != 1 || (unsigned) (pm->nrows * pm->ncols) != f->psize) return false;
+                rows[nf] = (int) pm->nrows; cols[nf] = (int) pm->ncols;
+            } else if ((MORPHO_ISNIL(f->prototype) || MORPHO_ISNUMBER(f->prototype)) && f->psize == 1) { rows[nf] = 0; cols[nf] = 0; }
+            else return false;
+            flds[nf++] = f;
+        }
+    }
+    mc_mirror *mr = mirror_get(info.mesh, g);
+    if (!mr) return false;
+    if (!mesh_getconnectivityelement(info.mesh, 0, g)) { morpho_runtimeerror(v, FUNC_ELNTFND, g); return true; }
+    mcu_expr_op prog[MC_MAXPROG];
+    int nops = 0;
+    const char *why = "";
+    if (!mc_translate_integrand(v, fn, mr->dim, nf, rows, cols, prog, MC_MAXPROG, &nops, &why)) {
+        mc_log("integrand not translated:", why);
+        return false;
+    }
+    mc_stat_translated++;
+    mcu_field *df[16];
+    for (int i = 0; i < nf; i++) { df[i] = field_get(flds[i], mr); if (!df[i]) return false; }
+    mcu_selection *sel = NULL;
+    if (info.sel) {
+        int *ids, n = selection_ids(info.sel, g, &ids);
+        if (n < 0) return false;
+        sel = mcu_selection_create(mr->m, g, n, ids);
+        free(ids);
+        if (!sel) return false;
+    }
+    int rc;
+    double total = 0.0;
+    objectmatrix *new = NULL;
+    if (mode == MCU_TOTAL) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_TOTAL, &total);
+    else {
+        objectsparse *s = mesh_getconnectivityelement(info.mesh, 0, g);
+        new = matrix_new(1, (MatrixIdx_t) s->ccs.ncols, false);
+        if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
+        else if (s->ccs.ncols > 0) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_INTEGRAND, new->elements);
+        else rc = MCU_OK;
+    }
+    if (sel) mcu_selection_destroy(sel);
+    if (rc == MCU_OK) {
+        mc_stat_evals++;
+        if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
+        else { *out = MORPHO_OBJECT(new); morpho_bindobjects(v, 1, out); }
+        return true;
+    }
+    if (new) object_free((object *) new);
+    if (rc == -1) return true;
+    mc_log("integral not accelerated:", mcu_last_error());
+    return false;
+}
+
+#define MC_IVENEER(cls, GRADE, meth, MODE) \
+    static builtinfunction orig_##cls##_##meth = NULL; \
+    static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
+        value out; \
+        if (mc_eval_integral(v, nargs, args, GRADE, MODE, &out)) return out; \
+        mc_stat_fallbacks++; \
+        return orig_##cls##_##meth(v, nargs, args); \
+    }
+MC_IVENEER(LineIntegral, MESH_GRADE_LINE, total, MCU_TOTAL)
+MC_IVENEER(LineIntegral, MESH_GRADE_LINE, integrand, MCU_INTEGRAND)
+MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, total, MCU_TOTAL)
+MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, integrand, MCU_INTEGRAND)
+
 #define MC_VENEER(cls, FID, GRADE, meth, MODE) \
     static builtinfunction orig_##cls##_##meth = NULL; \
     static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
@@ -497,14 +595,55 @@ static void mc_meshfree(object *obj) {
 
 /* ------------------------------------------------------------------ script-visible helpers */
 
-/* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference, field uploads] */
+/* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference, field uploads,
+ * integrand closures translated] */
 static value mc_stats(vm *v, int nargs, value *args) {
-    value vals[5] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
+    value vals[6] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
                      MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks),
-                     MORPHO_INTEGER((int) mc_stat_field_uploads)};
-    objectlist *l = object_newlist(5, vals);
+                     MORPHO_INTEGER((int) mc_stat_field_uploads), MORPHO_INTEGER((int) mc_stat_translated)};
+    objectlist *l = object_newlist(6, vals);
     if (!l) return MORPHO_NIL;
     return morpho_wrapandbind(v, (object *) l);
+}
+
+/* cudatranslate(f, dim, shapes): the postfix program the integrand f(x, q...) translates to, as a List of [op, a, c]
+ * triples, or a String saying why it cannot be translated.  shapes: one entry per quantity, 0 for a scalar, n for an
+ * n x 1 column vector, [r, c] for a matrix.  Works without a GPU (diagnostics, tests). */
+static value mc_translate_fn(vm *v, int nargs, value *args) {
+    if (nargs != 3 || !MORPHO_ISINTEGER(MORPHO_GETARG(args, 1)) || !MORPHO_ISLIST(MORPHO_GETARG(args, 2))) {
+        morpho_runtimeerror(v, VM_INVALIDARGS, 3, nargs);
+        return MORPHO_NIL;
+    }
+    objectlist *sh = MORPHO_GETLIST(MORPHO_GETARG(args, 2));
+    int rows[16], cols[16], nf = 0;
+    for (unsigned int i = 0; i < sh->val.count && nf < 16; i++, nf++) {
+        value e = sh->val.data[i];
+        if (MORPHO_ISINTEGER(e)) { rows[nf] = MORPHO_GETINTEGERVALUE(e); cols[nf] = rows[nf] ? 1 : 0; }
+        else if (MORPHO_ISLIST(e) && MORPHO_GETLIST(e)->val.count == 2 && MORPHO_ISINTEGER(MORPHO_GETLIST(e)->val.data[0]) && MORPHO_ISINTEGER(MORPHO_GETLIST(e)->val.data[1])) {
+            rows[nf] = MORPHO_GETINTEGERVALUE(MORPHO_GETLIST(e)->val.data[0]); cols[nf] = MORPHO_GETINTEGERVALUE(MORPHO_GETLIST(e)->val.data[1]);
+        } else { morpho_runtimeerror(v, VM_INVALIDARGS, 3, nargs); return MORPHO_NIL; }
+    }
+    mcu_expr_op prog[MC_MAXPROG];
+    int nops = 0;
+    const char *why = "";
+    if (!mc_translate_integrand(v, MORPHO_GETARG(args, 0), MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 1)), nf, rows, cols, prog, MC_MAXPROG, &nops, &why)) {
+        value s = object_stringfromcstring(why, strlen(why));
+        return morpho_wrapandbind(v, MORPHO_GETOBJECT(s));
+    }
+    objectlist *out = object_newlist(0, NULL);
+    if (!out) return MORPHO_NIL;
+    value keep[MC_MAXPROG + 1];
+    int nkeep = 0;
+    for (int i = 0; i < nops; i++) {
+        value t[3] = {MORPHO_INTEGER(prog[i].op), MORPHO_INTEGER(prog[i].a), MORPHO_FLOAT(prog[i].c)};
+        objectlist *row = object_newlist(3, t);
+        if (!row) break;
+        list_append(out, MORPHO_OBJECT(row));
+        keep[nkeep++] = MORPHO_OBJECT(row);
+    }
+    keep[nkeep++] = MORPHO_OBJECT(out);
+    morpho_bindobjects(v, nkeep, keep);
+    return MORPHO_OBJECT(out);
 }
 
 /* ------------------------------------------------------------------ extension entry points */
@@ -516,6 +655,7 @@ void morphocuda_initialize(void) {
     mc_paranoid = getenv("MORPHO_CUDA_PARANOID") && atoi(getenv("MORPHO_CUDA_PARANOID")) != 0;
     mc_verbose = getenv("MORPHO_CUDA_VERBOSE") && atoi(getenv("MORPHO_CUDA_VERBOSE")) != 0;
     builtin_addfunction("cudastats", mc_stats, MORPHO_FN_ALLOCATES);
+    builtin_addfunction("cudatranslate", mc_translate_fn, MORPHO_FN_ALLOCATES);
     if (mcu_init(dev ? atoi(dev) : 0) != MCU_OK) {
         /* no CPU path of ours exists: without a usable GPU nothing is patched and the reference runs as shipped */
         fprintf(stderr, "[morphocuda] CUDA unavailable (%s): functionals stay on the reference builtins\n", mcu_last_error());
@@ -532,6 +672,8 @@ void morphocuda_initialize(void) {
     PATCH(Nematic, total); PATCH(Nematic, integrand); PATCH(Nematic, gradient); PATCH(Nematic, fieldgradient);
     PATCH(NematicElectric, total); PATCH(NematicElectric, integrand); PATCH(NematicElectric, gradient); PATCH(NematicElectric, fieldgradient);
     PATCH(LineCurvatureSq, total); PATCH(LineCurvatureSq, integrand); PATCH(LineCurvatureSq, gradient);
+    PATCH(LineIntegral, total); PATCH(LineIntegral, integrand);
+    PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand);
 
     int nhooks = 0;
     nhooks += hook_writers("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF);

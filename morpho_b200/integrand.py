@@ -11,11 +11,14 @@ from __future__ import annotations
 import numpy as np
 
 OPS = {"const": 0, "pos": 1, "field": 2, "add": 3, "sub": 4, "mul": 5, "div": 6, "neg": 7, "powi": 8, "sqrt": 9,
-       "sin": 10, "cos": 11, "exp": 12, "log": 13, "abs": 14}
+       "sin": 10, "cos": 11, "exp": 12, "log": 13, "abs": 14, "pow": 15, "tan": 16, "asin": 17, "acos": 18,
+       "atan": 19, "atan2": 20, "sinh": 21, "cosh": 22, "tanh": 23, "floor": 24, "ceil": 25, "log10": 26}
+BINARY = ("add", "sub", "mul", "div", "pow", "atan2")
 
 OP_DTYPE = np.dtype([("op", "<i4"), ("a", "<i4"), ("c", "<f8")])
 
-__all__ = ["Expr", "trace", "sqrt", "sin", "cos", "exp", "log", "OPS", "OP_DTYPE"]
+__all__ = ["Expr", "trace", "sqrt", "sin", "cos", "exp", "log", "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh",
+           "tanh", "floor", "ceil", "log10", "OPS", "OP_DTYPE"]
 
 
 class Expr:
@@ -54,9 +57,10 @@ class Expr:
     def __pow__(self, n):
         if isinstance(n, (int, np.integer)):
             return self._un("powi", int(n))
-        if float(n) == 0.5:
-            return self._un("sqrt")
-        raise TypeError("only integer powers and 0.5 are supported in device integrands")
+        return self._bin(n, "pow")
+
+    def __rpow__(self, base):
+        return self._bin(base, "pow", True)
 
 
 def _fn(name):
@@ -67,6 +71,12 @@ def _fn(name):
 
 
 sqrt, sin, cos, exp, log = _fn("sqrt"), _fn("sin"), _fn("cos"), _fn("exp"), _fn("log")
+tan, asin, acos, atan, sinh, cosh, tanh = (_fn(n) for n in ("tan", "asin", "acos", "atan", "sinh", "cosh", "tanh"))
+floor, ceil, log10 = _fn("floor"), _fn("ceil"), _fn("log10")
+
+
+def atan2(y, x):
+    return Expr.lift(y)._bin(x, "atan2")
 
 
 def trace(fn, dim, field_sizes):

@@ -3,7 +3,7 @@
  * its CLI lives in another repository that is not available here.
  * TEST INFRASTRUCTURE ONLY.
  *
- *   morpho6 [-wN] file.morpho
+ *   morpho6 [-wN] [-D] file.morpho        (-D: print the bytecode listing before running)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,9 +22,10 @@ static char *slurp(const char *path) {
 }
 
 int main(int argc, const char *argv[]) {
-    int nthreads = 0; const char *file = NULL;
+    int nthreads = 0, disasm = 0; const char *file = NULL;
     for (int i = 1; i < argc; i++) {
         if (strncmp(argv[i], "-w", 2) == 0) nthreads = atoi(argv[i] + 2);
+        else if (strcmp(argv[i], "-D") == 0) disasm = 1;
         else file = argv[i];
     }
     if (!file) { fprintf(stderr, "usage: morpho6 [-wN] file.morpho\n"); return 2; }
@@ -40,6 +41,7 @@ int main(int argc, const char *argv[]) {
     error err; error_init(&err);
     int rc = 0;
     if (morpho_compile(src, c, false, &err)) {
+        if (disasm) morpho_disassemble(v, p, NULL);
         if (!morpho_run(v, p)) {
             error *e = morpho_geterror(v);
             printf("Error '%s': %s\n", e->id ? e->id : "?", e->msg);

@@ -363,6 +363,18 @@ static bool refh_integrand(unsigned int dim, double *lambda, double *x, unsigned
             case 12: st[sp - 1] = exp(st[sp - 1]); break;
             case 13: st[sp - 1] = log(st[sp - 1]); break;
             case 14: st[sp - 1] = fabs(st[sp - 1]); break;
+            case 15: sp--; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+            case 20: sp--; st[sp - 1] = atan2(st[sp - 1], st[sp]); break;
+            case 16: st[sp - 1] = tan(st[sp - 1]); break;
+            case 17: st[sp - 1] = asin(st[sp - 1]); break;
+            case 18: st[sp - 1] = acos(st[sp - 1]); break;
+            case 19: st[sp - 1] = atan(st[sp - 1]); break;
+            case 21: st[sp - 1] = sinh(st[sp - 1]); break;
+            case 22: st[sp - 1] = cosh(st[sp - 1]); break;
+            case 23: st[sp - 1] = tanh(st[sp - 1]); break;
+            case 24: st[sp - 1] = floor(st[sp - 1]); break;
+            case 25: st[sp - 1] = ceil(st[sp - 1]); break;
+            case 26: st[sp - 1] = log10(st[sp - 1]); break;
             default: return false;
         }
     }

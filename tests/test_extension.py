@@ -54,8 +54,74 @@ def test_extension_loads_and_is_inert_without_a_gpu(tmp_path):
     ref, _ = run(src, tmp_path, "stock.morpho")
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho")
     assert "CUDA unavailable" in err                 # loud, and nothing of ours computes on the CPU
-    assert new[-1].replace(" ", "") == "[0,0,0,0,0]"
+    assert new[-1].replace(" ", "") == "[0,0,0,0,0,0]"
     assert ref == new[:-1]
+
+
+def _run_program(prog, x, q):
+    """The postfix machine of include/morpho_cuda.h (mcu_expr_op), in Python."""
+    import math
+    un = {7: lambda a: -a, 9: math.sqrt, 10: math.sin, 11: math.cos, 12: math.exp, 13: math.log, 14: abs, 16: math.tan,
+          17: math.asin, 18: math.acos, 19: math.atan, 21: math.sinh, 22: math.cosh, 23: math.tanh,
+          24: lambda a: float(math.floor(a)), 25: lambda a: float(math.ceil(a)), 26: math.log10}
+    bi = {3: lambda a, b: a + b, 4: lambda a, b: a - b, 5: lambda a, b: a * b, 6: lambda a, b: a / b,
+          15: math.pow, 20: math.atan2}
+    st = []
+    for op, a, c in prog:
+        if op == 0:
+            st.append(c)
+        elif op == 1:
+            st.append(x[a])
+        elif op == 2:
+            st.append(q[a])
+        elif op == 8:
+            st.append(math.pow(st.pop(), float(a)))
+        elif op in bi:
+            r = st.pop()
+            l = st.pop()
+            st.append(bi[op](l, r))
+        else:
+            st.append(un[op](st.pop()))
+    assert len(st) == 1
+    return st[0]
+
+
+def test_closure_translator_reproduces_the_vm(tmp_path):
+    """mc_translate.h: every translated integrand, run as a postfix program, gives what the VM gives for the closure."""
+    out, _ = run(script("translate_closures.morpho"), tmp_path, "tr.morpho")
+    x = [[0.3, -0.7, 1.1], [-1.2, 0.4, 0.25]]
+    p = [0.45, -1.75]
+    qv = [[0.2, -1.3, 0.8], [1.5, 0.1, -0.6]]
+    tm = [[1.0, -0.3, 0.2, 0.7], [0.4, 0.9, -1.1, 0.05]]           # column-major 2x2
+    quantities = {"f0": lambda i: [], "f1": lambda i: [p[i]] + qv[i], "f2": lambda i: qv[i], "f3": lambda i: qv[i],
+                  "f4": lambda i: [], "f5": lambda i: tm[i], "f6": lambda i: [], "f7": lambda i: [], "f8": lambda i: [p[i]]}
+    progs, vals, fails = {}, {}, {}
+    for line in out:
+        w = line.split()
+        if w[0] == "PROG":
+            nums = w[2:]
+            progs[w[1]] = [(int(nums[i]), int(nums[i + 1]), float(nums[i + 2])) for i in range(0, len(nums), 3)]
+        elif w[0] == "VAL":
+            vals[w[1]] = [float(w[2]), float(w[3])]
+        elif w[0] == "FAIL":
+            fails[w[1]] = " ".join(w[2:])
+    assert sorted(progs) == sorted(quantities) == sorted(vals), (sorted(progs), fails)
+    for name, prog in progs.items():
+        for i in range(2):
+            got = _run_program(prog, x[i], quantities[name](i))
+            assert abs(got - vals[name][i]) <= 4e-15 * max(1.0, abs(vals[name][i])), (name, i, got, vals[name][i])
+    assert sorted(fails) == ["g0", "g1", "g2", "g3", "g4", "g5", "g6"], fails      # left to the reference builtin
+
+
+@pytest.mark.gpu
+def test_integral_closures_run_on_the_gpu(tmp_path):
+    src = script("integrals.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    stats = [int(v) for v in NUM.findall(new[-1])]
+    evals, fallbacks, translated = stats[0], stats[3], stats[5]
+    assert translated == 20 and evals >= 20 and fallbacks == 2, (stats, err)    # 8x2 + 4 selections; 2 untranslatable
+    compare(ref, new[:-1], 1e-12)
 
 
 @pytest.mark.gpu
@@ -68,7 +134,7 @@ def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
                    {"MORPHO_CUDA_VERBOSE": "1"})
     assert "ready:" in err, err
     stats = [int(x) for x in NUM.findall(new[-1])]
-    evals, vert_uploads, conn_uploads, fallbacks, field_uploads = stats
+    evals, vert_uploads, conn_uploads, fallbacks, field_uploads = stats[:5]
     assert evals > 0, (stats, err)
     compare(ref, new[:-1], tol)
     # the mirror is re-uploaded only when the VM wrote to it: far fewer uploads than evaluations in the optimisers

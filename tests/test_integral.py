@@ -31,7 +31,7 @@ def test_tracer_programs_are_well_formed():
         for op, a, c in prog.tolist():
             if op in (OPS["const"], OPS["pos"], OPS["field"]):
                 depth += 1
-            elif OPS["add"] <= op <= OPS["div"]:
+            elif OPS["add"] <= op <= OPS["div"] or op in (OPS["pow"], OPS["atan2"]):
                 assert depth >= 2, name
                 depth -= 1
             else:
