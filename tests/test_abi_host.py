@@ -97,10 +97,15 @@ def _decode_patch(P, h):
     patch_index = int(tab[0])
     gids = tab[4: 4 + 32 * n_slices].view(np.int32)
     noff = (n_slices + 4) & ~3
-    offs = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
+    offs_raw = tab[4 + 32 * n_slices: 4 + 32 * n_slices + noff].view(np.int32)[: n_slices + 1]
+    offs = offs_raw & ~31                                      # bit 0 of an offset marks a CLEAN slice
     ents = tab[4 + 32 * n_slices + noff:].view(np.uint16)[: int(offs[-1])]
     assert int(tab[2]) == 0 and int(tab[3]) == 0              # push list of the multi-GPU exchange: none attached
     assert offs[0] == 0 and len(ents) == offs[-1] and np.all(np.diff(offs) % 32 == 0) and np.all(np.diff(offs) >= 128)
+    for sl in range(n_slices):                                  # CLEAN: 32 real vertices, no START flag and no padding after entry 1
+        blk = ents[offs[sl]: offs[sl + 1]].reshape(-1, 32)
+        clean = bool(np.all(gids[32 * sl: 32 * sl + 32] >= 0)) and not np.any(blk[2:] & 0x8000)
+        assert bool(offs_raw[sl] & 1) == clean, (sl, clean)
     return slot_gid, gids, offs, ents, patch_index
 
 
