@@ -165,6 +165,12 @@ enum {
 typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
 int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                  mcu_selection *sel, int mode, double *host_out);
+/* LineIntegral/AreaIntegral gradient and fieldgradient: central differences over the quadrature, as the reference
+ * (functional_mapnumericalgradient / functional_mapnumericalfieldgradient, functional.c:1142-1247, 1305-1503 with
+ * lineintegral_integrand / areaintegral_integrand).  wrt < 0: positions (nv * dim doubles); wrt = k: the k-th field
+ * (nv * psize_k doubles, the layout of the Field's store). */
+int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                          mcu_selection *sel, int wrt, double *host_out);
 
 /* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.
  *      kind 0: Coulomb f=1/r, f'=-1/r^2 (examples/thomson/thomson.morpho:26).

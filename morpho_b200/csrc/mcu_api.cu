@@ -242,7 +242,7 @@ void mcu_host_transpose(int nv, int n, int nvper, const int *rix, const int *eid
 
 extern "C" {
 
-static int ensure_transpose(mcu_mesh *m, int g) {
+int mcu_ensure_transpose(mcu_mesh *m, int g) {
     McuConn &c = m->conn[g];
     if (c.d_tptr) return MCU_OK;
     std::vector<int> tptr, tidx;
@@ -257,7 +257,7 @@ static int ensure_transpose(mcu_mesh *m, int g) {
 
 int mcu_mesh_get_transpose(mcu_mesh *m, int g, int *tptr, int *tidx) {
     if (!m || g < 1 || g > 3 || !m->conn[g].present) { mcu_set_error("no elements of grade %d", g); return MCU_ERR_ELNOTFOUND; }
-    int rc = ensure_transpose(m, g);
+    int rc = mcu_ensure_transpose(m, g);
     if (rc) return rc;
     McuConn &c = m->conn[g];
     CK(cudaMemcpyAsync(tptr, c.d_tptr, sizeof(int) * ((size_t) m->nv + 1), cudaMemcpyDeviceToHost, g_stream));
@@ -484,13 +484,13 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
     }
     if (F == MCU_F_LINECURVATURESQ) {
         if (!m->conn[1].present) { mcu_set_error("LineCurvatureSq needs line elements"); return MCU_ERR_ELNOTFOUND; }
-        int rc = ensure_transpose(m, 1);
+        int rc = mcu_ensure_transpose(m, 1);
         if (rc) return rc;
         v.lrix = m->conn[1].d_rix; v.ltptr = m->conn[1].d_tptr; v.ltidx = m->conn[1].d_tidx;
     }
     const bool gather = (mode == MCU_GRADIENT || mode == MCU_FIELDGRADIENT) && g > 0;
     if (gather && !sel) {
-        int rc = ensure_transpose(m, g);
+        int rc = mcu_ensure_transpose(m, g);
         if (rc) return rc;
         v.tptr = m->conn[g].d_tptr; v.tidx = m->conn[g].d_tidx;
     }

@@ -56,6 +56,7 @@ void mcu_host_transpose(int nv, int n, int nvper, const int *rix, const int *eid
 // patch decomposition (mcu_patch.cu)
 McuPatchSet *mcu_patchset_build(int nv, int nel, const int *h_rix, const double *h_vert, cudaStream_t st);
 void mcu_patchset_free(McuPatchSet *ps);
+extern "C" int mcu_ensure_transpose(mcu_mesh *m, int g);       // builds conn[g].d_tptr / d_tidx if absent
 extern "C" int mcu_ensure_selection(mcu_selection *s);   // uploads ids / transpose / mask of a selection if stale
 int mcu_ensure_patches(mcu_mesh *m, int g);        // builds conn[g].patches if absent (MCU_ERR_UNSUPPORTED if it cannot)
 struct McuHaloPush;

@@ -191,17 +191,8 @@ __device__ double mi_tri(const MiView &v, const double (*xv)[3], const double (*
     return sum;
 }
 
-__global__ void __launch_bounds__(128) k_integral(MiView v, double *out) {
-    int ce = blockIdx.x * 128 + threadIdx.x;
-    if (ce >= v.n) return;
-    const int e = v.eids ? v.eids[ce] : ce;
-    const int nv = v.g + 1;
-    double xv[3][3], qv[3][MI_MAXQ];
-    for (int k = 0; k < nv; k++) {
-        const int id = v.rix[(size_t) e * nv + k];
-        for (int j = 0; j < 3; j++) xv[k][j] = (j < v.dim) ? v.vert[(size_t) id * v.dim + j] : 0.0;
-        for (int i = 0; i < v.nq; i++) qv[k][i] = v.fld[i][(size_t) id * v.fstride[i] + v.fcomp[i]];
-    }
+// integral over one element times its size: "*out *= elref.elementsize" (functional.c:5227, 5410)
+__device__ __forceinline__ double mi_element(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
     double val, size;
     if (v.g == 1) {
         val = mi_line(v, xv, qv);
@@ -211,7 +202,67 @@ __global__ void __launch_bounds__(128) k_integral(MiView v, double *out) {
         val = mi_tri(v, xv, qv);
         size = area_of(xv);
     }
-    out[e] = val * size;                               // "*out *= elref.elementsize" (functional.c:5227, 5410)
+    return val * size;
+}
+
+__device__ __forceinline__ void mi_gather(const MiView &v, int e, double (*xv)[3], double (*qv)[MI_MAXQ]) {
+    const int nv = v.g + 1;
+    for (int k = 0; k < nv; k++) {
+        const int id = v.rix[(size_t) e * nv + k];
+        for (int j = 0; j < 3; j++) xv[k][j] = (j < v.dim) ? v.vert[(size_t) id * v.dim + j] : 0.0;
+        for (int i = 0; i < v.nq; i++) qv[k][i] = v.fld[i][(size_t) id * v.fstride[i] + v.fcomp[i]];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_integral(MiView v, double *out) {
+    int ce = blockIdx.x * 128 + threadIdx.x;
+    if (ce >= v.n) return;
+    const int e = v.eids ? v.eids[ce] : ce;
+    double xv[3][3], qv[3][MI_MAXQ];
+    mi_gather(v, e, xv, qv);
+    out[e] = mi_element(v, xv, qv);
+}
+
+// Central differences of one element with respect to one of its vertices: the coordinates (qbase < 0) or the ncomp
+// components of a field stored there (functional_numericalgrad, functional.c:1142-1162; functional_numericalfieldgrad,
+// 1305-1328): f(x0 + eps) and f(x0 - eps) are full adaptive quadratures.  One thread per (element, corner); the
+// results go to scratch[(ce * nv + corner) * ncomp + c] and are summed per vertex in ascending element id by
+// k_integral_gather — the order in which the reference accumulates them.
+__global__ void __launch_bounds__(128) k_integral_fd(MiView v, int qbase, int ncomp, double *scratch) {
+    const int nv = v.g + 1;
+    long t = (long) blockIdx.x * 128 + threadIdx.x;
+    if (t >= (long) v.n * nv) return;
+    const int ce = (int) (t / nv), corner = (int) (t - (long) ce * nv);
+    const int e = v.eids ? v.eids[ce] : ce;
+    double xv[3][3], qv[3][MI_MAXQ];
+    mi_gather(v, e, xv, qv);
+    for (int c = 0; c < ncomp; c++) {
+        double *slot = qbase < 0 ? &xv[corner][c] : &qv[corner][qbase + c];
+        const double f0 = *slot, eps = fdstepsize(f0);
+        *slot = f0 + eps;
+        const double fp = mi_element(v, xv, qv);
+        *slot = f0 - eps;
+        const double fm = mi_element(v, xv, qv);
+        *slot = f0;
+        scratch[((size_t) ce * nv + corner) * ncomp + c] = (fp - fm) / (2 * eps);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_integral_gather(int nvtx, int nv, int ncomp, const int *__restrict__ tptr, const int *__restrict__ tidx,
+                                                         const int *__restrict__ eids, const int *__restrict__ rix,
+                                                         const double *__restrict__ scratch, double *__restrict__ out) {
+    int vtx = blockIdx.x * 128 + threadIdx.x;
+    if (vtx >= nvtx) return;
+    double acc[MI_MAXQ];
+    for (int c = 0; c < ncomp; c++) acc[c] = 0.0;
+    for (int q = tptr[vtx]; q < tptr[vtx + 1]; q++) {
+        const int ce = tidx[q], e = eids ? eids[ce] : ce;
+        int corner = 0;
+        for (int j = 0; j < nv; j++) if (rix[(size_t) e * nv + j] == vtx) corner = j;
+        const double *src = scratch + ((size_t) ce * nv + corner) * ncomp;
+        for (int c = 0; c < ncomp; c++) acc[c] = acc[c] + src[c];
+    }
+    for (int c = 0; c < ncomp; c++) out[(size_t) vtx * ncomp + c] = acc[c];
 }
 
 static __global__ void __launch_bounds__(256) k_isum(const double *__restrict__ v, int n, CompSum *partials) {
@@ -267,21 +318,19 @@ static void make_rules(MiRules &R) {
     node(3, 3, 3, 9);
 }
 
-extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
-                            mcu_selection *sel, int mode, double *host_out) {
-    if (!m || (grade != 1 && grade != 2) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0 || !host_out ||
-        (mode != MCU_TOTAL && mode != MCU_INTEGRAND)) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
+// arguments shared by mcu_integral and mcu_integral_gradient: validates, uploads the rules and the program, fills the view
+static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                          mcu_selection *sel, MiView &v, cudaStream_t st) {
+    if (!m || (grade != 1 && grade != 2) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
     if (!m->conn[grade].present) { mcu_set_error("mesh has no elements of grade %d", grade); return MCU_ERR_ELNOTFOUND; }
     if (sel && (sel->m != m || sel->g != grade)) { mcu_set_error("selection does not belong to this mesh / grade"); return MCU_ERR_ARGS; }
     static bool rules_up = false;
-    cudaStream_t st = mcu_stream();
     if (!rules_up) {
         MiRules R;
         make_rules(R);
         if (cudaMemcpyToSymbol(c_rules, &R, sizeof(R)) != cudaSuccess) { mcu_set_error("rule upload failed"); return MCU_ERR_CUDA; }
         rules_up = true;
     }
-    MiView v;
     memset(&v, 0, sizeof(v));
     v.dim = m->dim; v.g = grade; v.nops = nops; v.nel = m->conn[grade].nel;
     v.vert = m->d_vert; v.rix = m->conn[grade].d_rix;
@@ -289,7 +338,7 @@ extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op 
     v.eids = sel ? sel->d_eids : nullptr;
     v.n = sel ? (int) sel->ids.size() : v.nel;
     for (int f = 0; f < nfields; f++) {
-        if (!fields[f] || fields[f]->m != m) { mcu_set_error("field does not belong to this mesh"); return MCU_ERR_ARGS; }
+        if (!fields || !fields[f] || fields[f]->m != m) { mcu_set_error("field does not belong to this mesh"); return MCU_ERR_ARGS; }
         for (int c = 0; c < fields[f]->psize; c++) {
             if (v.nq == MI_MAXQ) { mcu_set_error("too many field components (max %d)", MI_MAXQ); return MCU_ERR_UNSUPPORTED; }
             v.fld[v.nq] = fields[f]->d_data; v.fstride[v.nq] = fields[f]->psize; v.fcomp[v.nq] = c; v.nq++;
@@ -309,6 +358,61 @@ extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op 
     }
     if (depth != 1) { mcu_set_error("integrand program leaves %d values", depth); return MCU_ERR_ARGS; }
     if (cudaMemcpyToSymbolAsync(c_prog, prog, sizeof(mcu_expr_op) * nops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return MCU_ERR_CUDA;
+    return MCU_OK;
+}
+
+/* Gradient of the integral by central differences, like the reference (LineIntegral/AreaIntegral gradient and
+ * fieldgradient are functional_mapnumericalgradient / functional_mapnumericalfieldgradient over the quadrature,
+ * functional.c:5240, 5319-5340, 5434-5458).  wrt < 0: vertex positions, host_out nv * dim doubles; wrt = k: the k-th
+ * field, host_out nv * psize_k doubles (the layout of that Field's store). */
+extern "C" int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                                     mcu_selection *sel, int wrt, double *host_out) {
+    if (!host_out || wrt >= nfields) { mcu_set_error("bad integral gradient arguments"); return MCU_ERR_ARGS; }
+    cudaStream_t st = mcu_stream();
+    MiView v;
+    int rc = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st);
+    if (rc) return rc;
+    int qbase = -1, ncomp = m->dim;
+    if (wrt >= 0) {
+        qbase = 0;
+        for (int f = 0; f < wrt; f++) qbase += fields[f]->psize;
+        ncomp = fields[wrt]->psize;
+    }
+    const int nv = grade + 1;
+    const int *tptr, *tidx;
+    if (sel) { tptr = sel->d_tptr; tidx = sel->d_tidx; }
+    else {
+        rc = mcu_ensure_transpose(m, grade);
+        if (rc) return rc;
+        tptr = m->conn[grade].d_tptr; tidx = m->conn[grade].d_tidx;
+    }
+    double *d_scratch = nullptr, *d_out = nullptr;
+    const size_t ns = (size_t) std::max(v.n, 1) * nv * ncomp, no = (size_t) m->nv * ncomp;
+    if (cudaMalloc((void **) &d_scratch, sizeof(double) * ns) != cudaSuccess || cudaMalloc((void **) &d_out, sizeof(double) * std::max<size_t>(no, 1)) != cudaSuccess) {
+        if (d_scratch) cudaFree(d_scratch);
+        mcu_set_error("integral gradient: allocation failed");
+        return MCU_ERR_ALLOC;
+    }
+    const long nt = (long) v.n * nv;
+    if (nt > 0) { k_integral_fd<<<(unsigned) ((nt + 127) / 128), 128, 0, st>>>(v, qbase, ncomp, d_scratch); g_mcu_launches += 1; }
+    k_integral_gather<<<(m->nv + 127) / 128, 128, 0, st>>>(m->nv, nv, ncomp, tptr, tidx, v.eids, v.rix, d_scratch, d_out);
+    g_mcu_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * no, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { mcu_set_error("integral gradient failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
+    cudaFree(d_scratch);
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                            mcu_selection *sel, int mode, double *host_out) {
+    if (!host_out || (mode != MCU_TOTAL && mode != MCU_INTEGRAND)) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
+    cudaStream_t st = mcu_stream();
+    MiView v;
+    int rc0 = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st);
+    if (rc0) return rc0;
     double *d_int = nullptr, *d_tot = nullptr;
     CompSum *d_part = nullptr;
     int rc = MCU_OK;

@@ -409,8 +409,10 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
     if (!functional_validateargs(v, nargs, args, &info)) return true;
     objectinstance *self = MORPHO_GETINSTANCE(MORPHO_SELF(args));
-    if (info.field || (info.sel && info.sel->mode != SELECT_SOME) || mesh_has_symmetries(info.mesh, g)) return false;
+    if ((info.field != NULL) != (mode == MCU_FIELDGRADIENT)) return false;
+    if ((info.sel && info.sel->mode != SELECT_SOME) || mesh_has_symmetries(info.mesh, g)) return false;
     value fn = MORPHO_NIL, val = MORPHO_NIL;
+    int wrt = -1;
     if (!prop(self, SCALARPOTENTIAL_FUNCTION_PROPERTY, &fn)) return false;
     if (prop(self, INTEGRAL_METHOD_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;            /* new integrator */
     if (prop(self, LINEARELASTICITY_REFERENCE_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;
@@ -430,9 +432,11 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
                 rows[nf] = (int) pm->nrows; cols[nf] = (int) pm->ncols;
             } else if ((MORPHO_ISNIL(f->prototype) || MORPHO_ISNUMBER(f->prototype)) && f->psize == 1) { rows[nf] = 0; cols[nf] = 0; }
             else return false;
+            if (f == info.field) wrt = nf;
             flds[nf++] = f;
         }
     }
+    if (mode == MCU_FIELDGRADIENT && wrt < 0) return false;      /* not one of the functional's fields: reference path */
     mc_mirror *mr = mirror_get(info.mesh, g);
     if (!mr) return false;
     if (!mesh_getconnectivityelement(info.mesh, 0, g)) { morpho_runtimeerror(v, FUNC_ELNTFND, g); return true; }
@@ -457,22 +461,33 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     int rc;
     double total = 0.0;
     objectmatrix *new = NULL;
+    objectfield *newf = NULL;
     if (mode == MCU_TOTAL) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_TOTAL, &total);
-    else {
+    else if (mode == MCU_INTEGRAND) {
         objectsparse *s = mesh_getconnectivityelement(info.mesh, 0, g);
         new = matrix_new(1, (MatrixIdx_t) s->ccs.ncols, false);
         if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
         else if (s->ccs.ncols > 0) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_INTEGRAND, new->elements);
         else rc = MCU_OK;
+    } else if (mode == MCU_GRADIENT) {
+        new = matrix_new(mr->dim, mr->nv, false);
+        if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
+        else rc = mcu_integral_gradient(mr->m, g, nops, prog, nf, df, sel, -1, new->elements);
+    } else {
+        objectfield *w = flds[wrt];
+        newf = object_newfield(info.mesh, w->prototype, w->fnspc, w->dof);           /* functional.c:1449 */
+        if (!newf || newf->data.nels != w->data.nels) { if (newf) object_free((object *) newf); newf = NULL; morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
+        else rc = mcu_integral_gradient(mr->m, g, nops, prog, nf, df, sel, wrt, newf->data.elements);
     }
     if (sel) mcu_selection_destroy(sel);
     if (rc == MCU_OK) {
         mc_stat_evals++;
         if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
-        else { *out = MORPHO_OBJECT(new); morpho_bindobjects(v, 1, out); }
+        else { *out = MORPHO_OBJECT(new ? (object *) new : (object *) newf); morpho_bindobjects(v, 1, out); }
         return true;
     }
     if (new) object_free((object *) new);
+    if (newf) object_free((object *) newf);
     if (rc == -1) return true;
     mc_log("integral not accelerated:", mcu_last_error());
     return false;
@@ -488,8 +503,12 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     }
 MC_IVENEER(LineIntegral, MESH_GRADE_LINE, total, MCU_TOTAL)
 MC_IVENEER(LineIntegral, MESH_GRADE_LINE, integrand, MCU_INTEGRAND)
+MC_IVENEER(LineIntegral, MESH_GRADE_LINE, gradient, MCU_GRADIENT)
+MC_IVENEER(LineIntegral, MESH_GRADE_LINE, fieldgradient, MCU_FIELDGRADIENT)
 MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, total, MCU_TOTAL)
 MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, integrand, MCU_INTEGRAND)
+MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, gradient, MCU_GRADIENT)
+MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, fieldgradient, MCU_FIELDGRADIENT)
 
 #define MC_VENEER(cls, FID, GRADE, meth, MODE) \
     static builtinfunction orig_##cls##_##meth = NULL; \
@@ -672,8 +691,8 @@ void morphocuda_initialize(void) {
     PATCH(Nematic, total); PATCH(Nematic, integrand); PATCH(Nematic, gradient); PATCH(Nematic, fieldgradient);
     PATCH(NematicElectric, total); PATCH(NematicElectric, integrand); PATCH(NematicElectric, gradient); PATCH(NematicElectric, fieldgradient);
     PATCH(LineCurvatureSq, total); PATCH(LineCurvatureSq, integrand); PATCH(LineCurvatureSq, gradient);
-    PATCH(LineIntegral, total); PATCH(LineIntegral, integrand);
-    PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand);
+    PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
+    PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
 
     int nhooks = 0;
     nhooks += hook_writers("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF);

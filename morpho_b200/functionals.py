@@ -218,8 +218,9 @@ class _Integral:
     """LineIntegral / AreaIntegral (functional.c:5186-5243, 5371-5426): the integral over every element of a callable
     of the position and of the interpolated field values, by the reference's default adaptive quadrature
     (integrate_integrate, integrate.c:769-800; mcu_integral.cu on the device).  ``fn(x, *q)`` is written with the
-    operators and functions of :mod:`morpho_b200.integrand`; it is recorded once into a postfix program.  Only
-    ``total`` and ``integrand`` exist on the device path (the reference's gradients re-enter the VM per FD probe)."""
+    operators and functions of :mod:`morpho_b200.integrand`; it is recorded once into a postfix program.
+    ``gradient`` / ``fieldgradient`` are central differences over the quadrature like the reference's
+    (functional_mapnumericalgradient / functional_mapnumericalfieldgradient, functional.c:1142-1247, 1305-1503)."""
     grade = 0
 
     def __init__(self, fn, *fields):
@@ -250,6 +251,28 @@ class _Integral:
 
     def integrand(self, *args):
         return self._eval(MCU_INTEGRAND, args)
+
+    def _grad(self, args, wrt):
+        mesh, sel, _ = Functional._args(args)
+        prog = self.program(mesh.dim)
+        if mesh.count(self.grade) == 0 and self.grade not in mesh._conn:
+            raise MorphoError(_lib.MCU_ERR_ELNOTFOUND, "FnctlELNtFnd", f"Mesh does not provide elements of grade {self.grade}.")
+        ncomp = mesh.dim if wrt < 0 else self.fields[wrt].psize
+        out = np.zeros((mesh.nv, ncomp), dtype=np.float64)
+        fh = (C.c_void_p * max(len(self.fields), 1))(*[f._h for f in self.fields])
+        hsel = sel._handle(self.grade) if sel is not None else None
+        check(lib().mcu_integral_gradient(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, wrt, out.ctypes.data))
+        return out
+
+    def gradient(self, *args):
+        return self._grad(args, -1)
+
+    def fieldgradient(self, field, *args):
+        """Gradient with respect to ``field``, which must be one of the Fields the integral was built with."""
+        for k, f in enumerate(self.fields):
+            if f is field:
+                return self._grad((field.mesh,) + tuple(args), k)
+        raise MorphoError(_lib.MCU_ERR_ARGS, "FnctlFldGrdArgs", "fieldgradient needs one of the functional's own fields")
 
 
 class LineIntegral(_Integral):

@@ -53,3 +53,9 @@ CASES = [
 
 def fields_for(vert):
     return _fields(vert)
+
+
+# gradients: (case name, wrt) with wrt = -1 for positions or the index of the field; evaluated through the VM by
+# LineIntegral/AreaIntegral(...).gradient(mesh) / .fieldgradient(field, mesh)
+GRAD_CASES = [("line_poly", -1), ("line_osc", -1), ("line_field", -1), ("line_field", 0), ("line_field", 1), ("line_sel", -1),
+              ("area_quad", -1), ("area_osc", -1), ("area_field", -1), ("area_field", 0), ("area_field", 1), ("area_sel", 0)]

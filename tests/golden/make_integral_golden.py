@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 from morpho_b200 import meshgen as mg  # noqa: E402
 from morpho_b200.integrand import trace  # noqa: E402
 from oracle.oracle import Reference  # noqa: E402
-from tests.golden.integral_cases import CASES, FIELD_SRC, fields_for, meshes  # noqa: E402
+from tests.golden.integral_cases import CASES, FIELD_SRC, GRAD_CASES, fields_for, meshes  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref")
 
@@ -42,6 +42,26 @@ def vm_integrands(tmp, ms):
         src.append(f"var r_{name} = {cls}({closure}{fargs}).integrand(m_{mesh})")
         src.append(f'print "@{name}"')
         src.append(f'for (i in 0...r_{name}.dimensions()[1]) print r_{name}[0,i].format("%.17g")')
+    bycase = {c[0]: c for c in CASES}
+    for gname, wrt in GRAD_CASES:
+        name, mesh, grade, _, closure, flds, sel = bycase[gname]
+        cls = "LineIntegral" if grade == 1 else "AreaIntegral"
+        fargs = "".join(f", {f}_{mesh}" for f in flds)
+        key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
+        selarg = ""
+        if sel is not None:
+            src.append(f"var s_{key} = Selection(m_{mesh})")
+            for i in sel:
+                src.append(f"s_{key}[{grade},{i}] = true")
+            selarg = f", s_{key}"
+        src.append(f'print "@{key}"')
+        if wrt < 0:
+            src.append(f"var g_{key} = {cls}({closure}{fargs}).gradient(m_{mesh}{selarg})")
+            src.append(f"var d_{key} = g_{key}.dimensions()")
+            src.append(f'for (i in 0...d_{key}[1]) for (k in 0...d_{key}[0]) print g_{key}[k,i].format("%.17g")')
+        else:
+            src.append(f"var g_{key} = {cls}({closure}{fargs}).fieldgradient({flds[wrt]}_{mesh}, m_{mesh}{selarg})")
+            src.append(f'for (x in g_{key}) {{ if (ismatrix(x)) {{ for (y in x) print y.format("%.17g") }} else print x.format("%.17g") }}')
     path = os.path.join(tmp, "integrals.morpho")
     open(path, "w").write("\n".join(src) + "\n")
     env = dict(os.environ, HOME=os.path.join(REF, "home"), OPENBLAS_NUM_THREADS="1")
@@ -77,6 +97,10 @@ def main():
         print(f"{name:12s} n={g.size:5d} sum={g.sum():+.15e}  VM closure vs harness bytecode: {err:.2e}")
         assert err < 1e-13, name
         store[name] = g
+    for gname, wrt in GRAD_CASES:
+        key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
+        store[key] = vm[key]
+        print(f"{key:28s} n={vm[key].size:5d} |g|={np.linalg.norm(vm[key]):.15e}")
     np.savez_compressed(os.path.join(HERE, "integrals.npz"), **store)
     print("wrote integrals.npz")
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.integral_cases import CASES, fields_for, meshes
+from tests.golden.integral_cases import CASES, GRAD_CASES, fields_for, meshes
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "integrals.npz")
 TOL = 1e-12
@@ -110,6 +110,29 @@ def test_device_quadrature_matches_vm_goldens(mb, case):
         c = (tt - s) - yy
         s = tt
     assert abs(total - s) <= TOL * max(abs(s), scale), case[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gcase", GRAD_CASES, ids=[f"{n}-{'x' if w < 0 else w}" for n, w in GRAD_CASES])
+def test_device_integral_gradients_match_vm_goldens(mb, gcase):
+    """gradient / fieldgradient = central differences over the quadrature (functional.c:1142-1162, 1305-1328): the
+    reference's values carry ~1e-10 of round-off amplified by 1/(2 eps), hence the finite-difference tolerance of
+    tests/parity.py (2e-9 of the gradient scale)."""
+    gname, wrt = gcase
+    case = next(c for c in CASES if c[0] == gname)
+    name, mesh, grade, fn, _, flds, sel = case
+    gold = np.load(GOLD)[f"grad__{gname}__{'x' if wrt < 0 else wrt}"]
+    v, gr = meshes()[mesh]
+    fd = fields_for(v)
+    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2))
+    fl = [mb.Field(m, fd[f]) for f in flds]
+    func = (mb.LineIntegral if grade == 1 else mb.AreaIntegral)(fn, *fl)
+    args = [m] + ([mb.Selection(m, ids={grade: sel})] if sel is not None else [])
+    got = func.gradient(*args) if wrt < 0 else func.fieldgradient(fl[wrt], *args[1:])
+    assert got.size == gold.size
+    err = np.max(np.abs(got.ravel() - gold)) / np.max(np.abs(gold))
+    print(gname, wrt, f"err {err:.2e}")
+    assert err <= 2e-9
 
 
 @pytest.mark.gpu
