@@ -160,7 +160,11 @@ enum {
     MCU_X_LOG = 13, MCU_X_ABS = 14,
     MCU_X_POW = 15 /* binary: pow(l, r) */, MCU_X_TAN = 16, MCU_X_ASIN = 17, MCU_X_ACOS = 18, MCU_X_ATAN = 19,
     MCU_X_ATAN2 = 20 /* binary: atan2(l, r) */, MCU_X_SINH = 21, MCU_X_COSH = 22, MCU_X_TANH = 23, MCU_X_FLOOR = 24,
-    MCU_X_CEIL = 25, MCU_X_LOG10 = 26
+    MCU_X_CEIL = 25, MCU_X_LOG10 = 26,
+    /* element constants, the helper builtins of functional.c:4396-4745: a = component of the unit tangent of a line
+     * element / the unit normal of a triangle in 3D; MCU_X_GRADQ a = 3 * (flattened field component) + k is the
+     * derivative along x_k of the P1 interpolant of that component on a triangle (gradsq_evaluategradient) */
+    MCU_X_TANGENT = 27, MCU_X_NORMAL = 28, MCU_X_GRADQ = 29
 };
 typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
 int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,

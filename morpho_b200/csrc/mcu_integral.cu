@@ -26,10 +26,12 @@
 #include <vector>
 
 #include "mcu_host.h"
+#include "mcu_integrands.cuh"      // perpendicular / p1grad_tri: the P1 gradient of GradSq, reused by grad()
 
 extern long g_mcu_launches;
 
-#define MI_MAXQ 16        // interpolated field components
+#define MI_MAXQ 40        // interpolated field components + element constants (tangent / normal / gradients)
+#define MI_MAXG 12        // field components whose gradient the integrand uses
 #define MI_MAXOPS 256
 #define MI_STACK 24       // expression stack
 #define MI_MAXDEPTH_LINE 30
@@ -52,6 +54,11 @@ struct MiView {
     int n;                                     // elements to visit
     const double *fld[MI_MAXQ];                // per flattened component: field base pointer
     int fstride[MI_MAXQ], fcomp[MI_MAXQ];      // psize of that field, component inside an entry
+    // Element constants are carried as extra "quantities" with the same value at every vertex (their interpolant is
+    // the constant): slots nq_in .. nq-1, filled by mi_derive from the (possibly perturbed) vertex data.
+    int nq_in;                                 // components read from fields; the rest are derived
+    int tn_slot;                               // first of 3 slots holding the tangent (g = 1) / normal (g = 2), or -1
+    int ngrad, gsrc[MI_MAXG], gslot[MI_MAXG];  // gradient of component gsrc[i] in slots gslot[i] .. +2
 };
 
 __device__ __forceinline__ double mi_eval(const MiView &v, const double *x, const double *q) {
@@ -191,8 +198,32 @@ __device__ double mi_tri(const MiView &v, const double (*xv)[3], const double (*
     return sum;
 }
 
+// tangent() / normal() / grad(q) of the element (integral_evaluatetangent, integral_evaluatenormal,
+// integral_evaluategradient → gradsq_evaluategradient; functional.c:4402-4425, 4444-4470, 4716-4726)
+__device__ __forceinline__ void mi_derive(const MiView &v, const double (*xv)[3], double (*qv)[MI_MAXQ]) {
+    const int nv = v.g + 1;
+    if (v.tn_slot >= 0) {
+        double t[3];
+        if (v.g == 1) { t[0] = xv[1][0] - xv[0][0]; t[1] = xv[1][1] - xv[0][1]; t[2] = xv[1][2] - xv[0][2]; }
+        else {
+            const double s0[3] = {xv[1][0] - xv[0][0], xv[1][1] - xv[0][1], xv[1][2] - xv[0][2]};
+            const double s1[3] = {xv[2][0] - xv[1][0], xv[2][1] - xv[1][1], xv[2][2] - xv[1][2]};
+            cross3(s0, s1, t);
+        }
+        const double nrm = sqrt(dot3(t, t));
+        if (fabs(nrm) > MCU_EPS) { const double r = 1.0 / nrm; t[0] *= r; t[1] *= r; t[2] *= r; }
+        for (int k = 0; k < nv; k++) for (int j = 0; j < 3; j++) qv[k][v.tn_slot + j] = t[j];
+    }
+    for (int i = 0; i < v.ngrad; i++) {
+        double vals[3] = {qv[0][v.gsrc[i]], qv[1][v.gsrc[i]], qv[2][v.gsrc[i]]}, gr[3] = {0.0, 0.0, 0.0};
+        p1grad_tri(v.dim, xv, 1, vals, 1, gr);
+        for (int k = 0; k < nv; k++) for (int j = 0; j < 3; j++) qv[k][v.gslot[i] + j] = gr[j];
+    }
+}
+
 // integral over one element times its size: "*out *= elref.elementsize" (functional.c:5227, 5410)
-__device__ __forceinline__ double mi_element(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
+__device__ __forceinline__ double mi_element(const MiView &v, const double (*xv)[3], double (*qv)[MI_MAXQ]) {
+    if (v.nq > v.nq_in) mi_derive(v, xv, qv);
     double val, size;
     if (v.g == 1) {
         val = mi_line(v, xv, qv);
@@ -210,7 +241,7 @@ __device__ __forceinline__ void mi_gather(const MiView &v, int e, double (*xv)[3
     for (int k = 0; k < nv; k++) {
         const int id = v.rix[(size_t) e * nv + k];
         for (int j = 0; j < 3; j++) xv[k][j] = (j < v.dim) ? v.vert[(size_t) id * v.dim + j] : 0.0;
-        for (int i = 0; i < v.nq; i++) qv[k][i] = v.fld[i][(size_t) id * v.fstride[i] + v.fcomp[i]];
+        for (int i = 0; i < v.nq_in; i++) qv[k][i] = v.fld[i][(size_t) id * v.fstride[i] + v.fcomp[i]];
     }
 }
 
@@ -344,10 +375,33 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
             v.fld[v.nq] = fields[f]->d_data; v.fstride[v.nq] = fields[f]->psize; v.fcomp[v.nq] = c; v.nq++;
         }
     }
-    // validate the program: stack discipline and operand ranges
+    // validate the program (stack discipline, operand ranges) and give the element constants it uses their slots
+    v.nq_in = v.nq;
+    v.tn_slot = -1;
+    std::vector<mcu_expr_op> rw(prog, prog + nops);
     int depth = 0;
     for (int i = 0; i < nops; i++) {
-        const mcu_expr_op &op = prog[i];
+        mcu_expr_op &op = rw[i];
+        if (op.op == MCU_X_TANGENT || op.op == MCU_X_NORMAL) {
+            // the reference raises TNGNT_GRD / NRML_GRD on the wrong grade; veccross needs three coordinates
+            if (op.a < 0 || op.a > 2 || (op.op == MCU_X_TANGENT ? grade != 1 : (grade != 2 || m->dim != 3))) { mcu_set_error("tangent()/normal() not defined for this grade"); return MCU_ERR_UNSUPPORTED; }
+            if (v.tn_slot < 0) {
+                if (v.nq + 3 > MI_MAXQ) { mcu_set_error("too many integrand quantities"); return MCU_ERR_UNSUPPORTED; }
+                v.tn_slot = v.nq; v.nq += 3;
+            }
+            op.op = MCU_X_FIELD; op.a = v.tn_slot + op.a;
+        } else if (op.op == MCU_X_GRADQ) {
+            const int comp = op.a / 3, k = op.a % 3;
+            if (grade != 2 || op.a < 0 || comp >= v.nq_in || k >= m->dim) { mcu_set_error("grad() needs a triangle and a field component"); return MCU_ERR_UNSUPPORTED; }
+            int gi = -1;
+            for (int j = 0; j < v.ngrad; j++) if (v.gsrc[j] == comp) gi = j;
+            if (gi < 0) {
+                if (v.ngrad == MI_MAXG || v.nq + 3 > MI_MAXQ) { mcu_set_error("too many gradients in the integrand"); return MCU_ERR_UNSUPPORTED; }
+                gi = v.ngrad++;
+                v.gsrc[gi] = comp; v.gslot[gi] = v.nq; v.nq += 3;
+            }
+            op.op = MCU_X_FIELD; op.a = v.gslot[gi] + k;
+        }
         if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
             if ((op.op == MCU_X_POS && (op.a < 0 || op.a > 2)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= v.nq))) { mcu_set_error("integrand operand out of range at op %d", i); return MCU_ERR_ARGS; }
             depth++;
@@ -357,7 +411,9 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
         if (depth > MI_STACK) { mcu_set_error("integrand stack too deep"); return MCU_ERR_UNSUPPORTED; }
     }
     if (depth != 1) { mcu_set_error("integrand program leaves %d values", depth); return MCU_ERR_ARGS; }
-    if (cudaMemcpyToSymbolAsync(c_prog, prog, sizeof(mcu_expr_op) * nops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return MCU_ERR_CUDA;
+    prog = rw.data();                           // lives on this frame: the copy below is completed before returning
+    if (cudaMemcpyToSymbolAsync(c_prog, prog, sizeof(mcu_expr_op) * nops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) return MCU_ERR_CUDA;
     return MCU_OK;
 }
 

@@ -7,8 +7,8 @@
  * Handled: straight-line code made of MOV LCT LGL LUP ADD SUB MUL DIV POW LIX CALL INVOKE RETURN (vm.c:924-1620 for
  * their semantics, incl. Int/Float promotion), calls of the real math builtins (functiondefs.c:659-695), calls of other
  * Morpho functions (inlined), element-wise vector arithmetic on the position / matrix-valued quantities, `norm`,
- * `inner`, `sum`, `trace`, `count`.  Anything else (branches, loops, lists, tangent()/normal()/grad(), printing,
- * writes to globals ...) makes the translation fail, and the caller runs the reference builtin instead.
+ * `inner`, `sum`, `trace`, `count`, and the element helpers tangent(), normal(), grad(q) (constants of the element).
+ * Anything else (branches, loops, lists, printing, writes to globals ...) makes the translation fail, and the caller runs the reference builtin instead.
  * Globals and upvalues are read at translation time; the translation is redone at every evaluation.
  */
 #ifndef MC_TRANSLATE_H
@@ -27,12 +27,14 @@
 #define MT_MAXDEPTH 6
 
 typedef struct { int op, a, b, isint; double c; } mt_node;        /* op: MCU_X_*;  CONST: c (isint: a Morpho Int) */
-typedef enum { MT_NONE, MT_NUM, MT_VEC, MT_OBJ } mt_kind;
-typedef struct { mt_kind kind; int nrows, ncols; int node[MT_MAXCOMP]; value obj; } mt_sym;
+typedef enum { MT_NONE, MT_NUM, MT_VEC, MT_OBJ, MT_GRADLIST } mt_kind;
+/* field >= 0: the symbol still IS the interpolated value of that Field argument (what grad() looks up, functional.c:4644-4652);
+ * qbase: its first flattened component.  MT_GRADLIST: grad(q) of a matrix-valued q, a List of dim matrices. */
+typedef struct { mt_kind kind; int nrows, ncols; int node[MT_MAXCOMP]; value obj; int field, qbase; } mt_sym;
 typedef struct {
     vm *v;
     mt_node nodes[MT_MAXNODES];
-    int nnodes, depth;
+    int nnodes, depth, dim;
     const char *why;
 } mt_ctx;
 
@@ -49,7 +51,7 @@ static int mt_consti(mt_ctx *c, int i) { return mt_new(c, MCU_X_CONST, i, 0, (do
 static bool mt_isconst(mt_ctx *c, int n) { return n >= 0 && c->nodes[n].op == MCU_X_CONST; }
 static bool mt_isint(mt_ctx *c, int n) { return mt_isconst(c, n) && c->nodes[n].isint; }
 
-static mt_sym mt_num(int node) { mt_sym s; memset(&s, 0, sizeof(s)); s.kind = node >= 0 ? MT_NUM : MT_NONE; s.node[0] = node; s.obj = MORPHO_NIL; return s; }
+static mt_sym mt_num(int node) { mt_sym s; memset(&s, 0, sizeof(s)); s.kind = node >= 0 ? MT_NUM : MT_NONE; s.node[0] = node; s.obj = MORPHO_NIL; s.field = -1; return s; }
 static mt_sym mt_none(void) { return mt_num(-1); }
 
 /* ADD SUB MUL DIV POW on two scalars, with the VM's Int/Float rules (vm.c:934-1075) and constant folding */
@@ -152,20 +154,20 @@ static bool mt_arith(mt_ctx *c, int op, const mt_sym *l, const mt_sym *r, mt_sym
     const int n = (l->kind == MT_VEC ? l : r)->nrows * (l->kind == MT_VEC ? l : r)->ncols;
     if (op == MCU_X_ADD || op == MCU_X_SUB) {
         if (!mt_sameshape(l, r)) return mt_fail(c, "vector arithmetic on operands of different kinds");
-        *out = *l;
+        *out = *l; out->field = -1;
         for (int i = 0; i < n; i++) if ((out->node[i] = mt_binary(c, op, l->node[i], r->node[i])) < 0) return false;
         return true;
     }
     if (op == MCU_X_MUL && ((l->kind == MT_VEC && r->kind == MT_NUM) || (l->kind == MT_NUM && r->kind == MT_VEC))) {
         const mt_sym *vec = l->kind == MT_VEC ? l : r, *s = l->kind == MT_VEC ? r : l;
-        *out = *vec;
+        *out = *vec; out->field = -1;
         for (int i = 0; i < n; i++) if ((out->node[i] = mt_binary(c, MCU_X_MUL, vec->node[i], s->node[0])) < 0) return false;   /* cblas_dscal: x[i]*s */
         return true;
     }
     if (op == MCU_X_DIV && l->kind == MT_VEC && r->kind == MT_NUM) {
         /* Matrix / scalar scales by the reciprocal (matrix.c: Matrix_div → scale by 1/x) */
         int inv = mt_binary(c, MCU_X_DIV, mt_constf(c, 1.0), r->node[0]);
-        *out = *l;
+        *out = *l; out->field = -1;
         for (int i = 0; i < n; i++) if ((out->node[i] = mt_binary(c, MCU_X_MUL, l->node[i], inv)) < 0) return false;
         return true;
     }
@@ -190,6 +192,15 @@ static int mt_sumsq(mt_ctx *c, const mt_sym *a, const mt_sym *b) {
 
 static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym *ret);
 
+/* grad(q)[k] for a matrix-valued q: a matrix shaped like q whose entries are d q_c / d x_k */
+static bool mt_gradlist_at(mt_ctx *c, const mt_sym *lst, int k, mt_sym *out) {
+    if (k < 0 || k >= c->dim) return mt_fail(c, "index out of bounds");
+    *out = mt_none();
+    out->kind = MT_VEC; out->nrows = lst->nrows; out->ncols = lst->ncols;
+    for (int i = 0; i < lst->nrows * lst->ncols; i++) if ((out->node[i] = mt_new(c, MCU_X_GRADQ, 3 * (lst->qbase + i) + k, 0, 0.0, 0)) < 0) return false;
+    return true;
+}
+
 /* OP_INVOKE on a vector: the Matrix methods an integrand typically uses */
 static bool mt_invoke(mt_ctx *c, const char *sel, const mt_sym *obj, const mt_sym *args, int nargs, mt_sym *out) {
     if (obj->kind != MT_VEC) return mt_fail(c, "method call on something that is not a matrix quantity");
@@ -208,7 +219,7 @@ static bool mt_invoke(mt_ctx *c, const char *sel, const mt_sym *obj, const mt_sy
     }
     if (!strcmp(sel, "count") && nargs == 0) { *out = mt_num(mt_consti(c, n)); return true; }
     if (!strcmp(sel, "transpose") && nargs == 0) {
-        *out = *obj; out->nrows = obj->ncols; out->ncols = obj->nrows;
+        *out = *obj; out->field = -1; out->nrows = obj->ncols; out->ncols = obj->nrows;
         for (int i = 0; i < obj->nrows; i++) for (int j = 0; j < obj->ncols; j++) out->node[j + i * obj->ncols] = obj->node[i + j * obj->nrows];
         return true;
     }
@@ -221,6 +232,24 @@ static bool mt_call(mt_ctx *c, const mt_sym *callee, const mt_sym *args, int nar
     if (MORPHO_ISFUNCTION(fn) || MORPHO_ISCLOSURE(fn)) return mt_interp(c, fn, args, nargs, out);
     const char *name = mt_builtinname(fn);
     if (!name) return mt_fail(c, "call of an unknown builtin");
+    /* element helpers (functional.c:4396-4745): constants of the element, leaves of the expression */
+    if (nargs == 0 && (!strcmp(name, "tangent") || !strcmp(name, "normal"))) {
+        *out = mt_none(); out->kind = MT_VEC; out->nrows = c->dim; out->ncols = 1;
+        for (int i = 0; i < c->dim; i++) out->node[i] = mt_new(c, name[0] == 't' ? MCU_X_TANGENT : MCU_X_NORMAL, i, 0, 0.0, 0);
+        return true;
+    }
+    if (nargs == 1 && !strcmp(name, "grad")) {
+        const mt_sym *q = &args[0];
+        if (q->field < 0) return mt_fail(c, "grad() of something that is not a Field argument");
+        *out = mt_none();
+        if (q->kind == MT_NUM) {                    /* scalar Field: a dim x 1 Matrix (integral_gradalloc) */
+            out->kind = MT_VEC; out->nrows = c->dim; out->ncols = 1;
+            for (int k = 0; k < c->dim; k++) out->node[k] = mt_new(c, MCU_X_GRADQ, 3 * q->qbase + k, 0, 0.0, 0);
+        } else {                                    /* Matrix prototype: a List of dim matrices, [k] = d q / d x_k */
+            out->kind = MT_GRADLIST; out->nrows = q->nrows; out->ncols = q->ncols; out->qbase = q->qbase;
+        }
+        return true;
+    }
     for (int i = 0; i < nargs; i++) if (args[i].kind != MT_NUM) return mt_fail(c, "builtin called with a non-numeric argument");
     if (nargs == 1) for (int k = 0; mt_unaryfns[k].name; k++) if (!strcmp(name, mt_unaryfns[k].name)) {
         *out = mt_num(mt_unary(c, mt_unaryfns[k].op, args[0].node[0]));
@@ -274,6 +303,12 @@ static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym
             case OP_LIX: {                          /* reg[b] = reg[a][reg[b] .. reg[c]]  (vm.c:1581-1609) */
                 const mt_sym *m = &reg[a];
                 int i = 0, j = 0, nidx = cc - b + 1, lin;
+                if (m->kind == MT_GRADLIST) {
+                    mt_sym g;
+                    if (nidx != 1 || !mt_constindex(c, &reg[b], &i) || !mt_gradlist_at(c, m, i, &g)) { mt_fail(c, "indexing grad()"); done = true; break; }
+                    reg[b] = g;
+                    break;
+                }
                 if (m->kind != MT_VEC || nidx < 1 || nidx > 2 || !mt_constindex(c, &reg[b], &i) || (nidx == 2 && !mt_constindex(c, &reg[cc], &j))) { mt_fail(c, "indexing"); done = true; break; }
                 if (nidx == 1) {                    /* Matrix_enumerate: the i-th stored element */
                     if (i < 0 || i >= m->nrows * m->ncols) { mt_fail(c, "index out of bounds"); done = true; break; }
@@ -283,6 +318,13 @@ static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym
                     lin = i + j * m->nrows;
                 }
                 reg[b] = mt_num(m->node[lin]);
+                break;
+            }
+            case OP_LIXL: {                         /* reg[a] = list reg[b] [ reg[c] ]  (vm.c:1611-1627) */
+                int i = 0;
+                mt_sym g;
+                if (reg[b].kind != MT_GRADLIST || !mt_constindex(c, &reg[cc], &i) || !mt_gradlist_at(c, &reg[b], i, &g)) { mt_fail(c, "list indexing"); done = true; break; }
+                reg[a] = g;
                 break;
             }
             case OP_CALL: {
@@ -326,7 +368,8 @@ static bool mt_emit(mt_ctx *c, int node, mcu_expr_op *prog, int *n, int cap) {
     while (sp > 0 && ok) {
         frame *f = &st[sp - 1];
         const mt_node *nd = &c->nodes[f->node];
-        const bool leaf = nd->op == MCU_X_CONST || nd->op == MCU_X_POS || nd->op == MCU_X_FIELD;
+        const bool leaf = nd->op == MCU_X_CONST || nd->op == MCU_X_POS || nd->op == MCU_X_FIELD || nd->op == MCU_X_TANGENT ||
+                          nd->op == MCU_X_NORMAL || nd->op == MCU_X_GRADQ;
         const bool binary = (nd->op >= MCU_X_ADD && nd->op <= MCU_X_DIV) || nd->op == MCU_X_POW || nd->op == MCU_X_ATAN2;
         if (sp >= MT_MAXNODES) { ok = mt_fail(c, "expression too deep"); break; }
         if (!leaf && f->stage == 0) {
@@ -338,7 +381,7 @@ static bool mt_emit(mt_ctx *c, int node, mcu_expr_op *prog, int *n, int cap) {
         if (binary && f->stage == 1) { f->stage = 2; st[sp].node = nd->b; st[sp++].stage = 0; continue; }
         if (*n >= cap) { ok = mt_fail(c, "integrand program too long"); break; }
         prog[*n].op = nd->op;
-        prog[*n].a = (nd->op == MCU_X_POS || nd->op == MCU_X_FIELD || nd->op == MCU_X_POWI) ? nd->a : 0;
+        prog[*n].a = ((leaf && nd->op != MCU_X_CONST) || nd->op == MCU_X_POWI) ? nd->a : 0;
         prog[*n].c = nd->op == MCU_X_CONST ? nd->c : 0.0;
         (*n)++;
         sp--;
@@ -353,6 +396,7 @@ static bool mc_translate_integrand(vm *v, value fn, int dim, int nfields, const 
     mt_ctx *c = (mt_ctx *) calloc(1, sizeof(mt_ctx));
     if (!c) { *why = "allocation"; return false; }
     c->v = v;
+    c->dim = dim;
     mt_sym args[1 + 16];
     bool ok = nfields <= 16;
     if (ok) {
@@ -364,12 +408,14 @@ static bool mc_translate_integrand(vm *v, value fn, int dim, int nfields, const 
             *s = mt_none();
             if (fieldrows[k] == 0) {                 /* scalar Field: the quantity is a Float */
                 *s = mt_num(mt_new(c, MCU_X_FIELD, q, 0, 0.0, 0));
+                s->field = k; s->qbase = q;
                 q += 1;
                 continue;
             }
             const int n = fieldrows[k] * fieldcols[k];
             if (n < 1 || n > MT_MAXCOMP) { ok = mt_fail(c, "field prototype too large"); break; }
             s->kind = MT_VEC; s->nrows = fieldrows[k]; s->ncols = fieldcols[k];
+            s->field = k; s->qbase = q;
             for (int i = 0; i < n; i++) s->node[i] = mt_new(c, MCU_X_FIELD, q + i, 0, 0.0, 0);
             q += n;
         }

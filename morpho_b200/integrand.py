@@ -12,13 +12,14 @@ import numpy as np
 
 OPS = {"const": 0, "pos": 1, "field": 2, "add": 3, "sub": 4, "mul": 5, "div": 6, "neg": 7, "powi": 8, "sqrt": 9,
        "sin": 10, "cos": 11, "exp": 12, "log": 13, "abs": 14, "pow": 15, "tan": 16, "asin": 17, "acos": 18,
-       "atan": 19, "atan2": 20, "sinh": 21, "cosh": 22, "tanh": 23, "floor": 24, "ceil": 25, "log10": 26}
+       "atan": 19, "atan2": 20, "sinh": 21, "cosh": 22, "tanh": 23, "floor": 24, "ceil": 25, "log10": 26,
+       "tangent": 27, "normal": 28, "gradq": 29}
 BINARY = ("add", "sub", "mul", "div", "pow", "atan2")
 
 OP_DTYPE = np.dtype([("op", "<i4"), ("a", "<i4"), ("c", "<f8")])
 
 __all__ = ["Expr", "trace", "sqrt", "sin", "cos", "exp", "log", "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh",
-           "tanh", "floor", "ceil", "log10", "OPS", "OP_DTYPE"]
+           "tanh", "floor", "ceil", "log10", "tangent", "normal", "grad", "OPS", "OP_DTYPE"]
 
 
 class Expr:
@@ -79,14 +80,48 @@ def atan2(y, x):
     return Expr.lift(y)._bin(x, "atan2")
 
 
+class _Q(Expr):
+    """The interpolated value of a scalar Field argument (what ``grad`` recognises)."""
+    __slots__ = ("qbase",)
+
+
+class _QVec(tuple):
+    """The interpolated value of a vector / matrix Field argument."""
+    qbase = 0
+
+
+def tangent():
+    """Unit tangent of the line element (the reference's ``tangent()``, functional.c:4402-4425)."""
+    return tuple(Expr([(OPS["tangent"], k, 0.0)]) for k in range(3))
+
+
+def normal():
+    """Unit normal of the triangle (the reference's ``normal()``, functional.c:4444-4470)."""
+    return tuple(Expr([(OPS["normal"], k, 0.0)]) for k in range(3))
+
+
+def grad(q):
+    """P1 gradient of a Field argument on the triangle (``grad(q)``, functional.c:4638-4745): for a scalar field a
+    tuple (d/dx0, d/dx1, d/dx2); for a vector field a list over the directions of tuples over the components."""
+    if isinstance(q, _Q):
+        return tuple(Expr([(OPS["gradq"], 3 * q.qbase + k, 0.0)]) for k in range(3))
+    if isinstance(q, _QVec):
+        return [tuple(Expr([(OPS["gradq"], 3 * (q.qbase + c) + k, 0.0)]) for c in range(len(q))) for k in range(3)]
+    raise TypeError("grad() takes a Field argument of the integrand")
+
+
 def trace(fn, dim, field_sizes):
     """Call ``fn`` with symbolic arguments and return its program as a structured numpy array."""
     x = tuple(Expr([(OPS["pos"], k, 0.0)]) for k in range(dim))
     args, q = [], 0
     for ps in field_sizes:
-        comps = tuple(Expr([(OPS["field"], q + k, 0.0)]) for k in range(ps))
+        if ps == 1:
+            a = _Q([(OPS["field"], q, 0.0)])
+        else:
+            a = _QVec(Expr([(OPS["field"], q + k, 0.0)]) for k in range(ps))
+        a.qbase = q
         q += ps
-        args.append(comps[0] if ps == 1 else comps)
+        args.append(a)
     out = Expr.lift(fn(x, *args))
     prog = np.zeros(len(out.prog), dtype=OP_DTYPE)
     for i, t in enumerate(out.prog):

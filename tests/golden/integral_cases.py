@@ -4,7 +4,7 @@ golden file is made.  Fields are polynomials of the vertex position so that both
 import numpy as np
 
 from morpho_b200 import meshgen as mg
-from morpho_b200.integrand import cos, exp, log, sin, sqrt
+from morpho_b200.integrand import cos, exp, grad, log, normal, sin, sqrt, tangent
 
 
 def _fields(vert):
@@ -48,6 +48,15 @@ CASES = [
     ("area_peak", "disk2d", 2, lambda x: 1.0 / (0.02 + (x[0] - 0.3) ** 2 + x[1] ** 2), "fn (x) 1/(0.02+(x[0]-0.3)^2+x[1]^2)", [], None),
     ("area_field", "sphere", 2, lambda x, p, q: p * p + q[0] * q[1] - q[2] * x[2], "fn (x, p, q) p*p+q[0]*q[1]-q[2]*x[2]", ["phi", "q"], None),
     ("area_sel", "sphere", 2, lambda x, q: sqrt(1.0 + q[1]) * exp(-x[2]), "fn (x, q) sqrt(1+q[1])*exp(-x[2])", ["q"], [1, 2, 17, 40, 41, 99, 150]),
+    # element helpers: tangent(), normal(), grad(q)
+    ("line_tangent", "loop", 1, lambda x: (tangent()[0] * x[1] - tangent()[2]) ** 2 + tangent()[1],
+     "fn (x) (tangent()[0]*x[1]-tangent()[2])^2+tangent()[1]", [], None),
+    ("area_anchor", "sphere", 2, lambda x, q: (q[0] * normal()[0] + q[1] * normal()[1] + q[2] * normal()[2]) ** 2 + normal()[2] * x[0],
+     "fn (x, q) q.inner(normal())^2+normal()[2]*x[0]", ["q"], None),
+    ("area_gradsq", "sphere", 2, lambda x, p: grad(p)[0] ** 2 + grad(p)[1] ** 2 + grad(p)[2] ** 2 + p * grad(p)[0],
+     "fn (x, p) grad(p).inner(grad(p))+p*grad(p)[0]", ["phi"], None),
+    ("area_gradvec", "sphere", 2, lambda x, q: sum(grad(q)[k][c] ** 2 for k in range(3) for c in range(3)) + grad(q)[1][0] * q[2],
+     "fn (x, q) { var g = grad(q); return g[0].inner(g[0])+g[1].inner(g[1])+g[2].inner(g[2])+g[1][0]*q[2] }", ["q"], None),
 ]
 
 
@@ -58,4 +67,6 @@ def fields_for(vert):
 # gradients: (case name, wrt) with wrt = -1 for positions or the index of the field; evaluated through the VM by
 # LineIntegral/AreaIntegral(...).gradient(mesh) / .fieldgradient(field, mesh)
 GRAD_CASES = [("line_poly", -1), ("line_osc", -1), ("line_field", -1), ("line_field", 0), ("line_field", 1), ("line_sel", -1),
-              ("area_quad", -1), ("area_osc", -1), ("area_field", -1), ("area_field", 0), ("area_field", 1), ("area_sel", 0)]
+              ("area_quad", -1), ("area_osc", -1), ("area_field", -1), ("area_field", 0), ("area_field", 1), ("area_sel", 0),
+              ("line_tangent", -1), ("area_anchor", -1), ("area_anchor", 0), ("area_gradsq", -1), ("area_gradsq", 0),
+              ("area_gradvec", 0)]

@@ -88,15 +88,18 @@ def main():
         v, gr = ms[mesh]
         fd = fields_for(v)
         prog = trace(fn, v.shape[1], [fd[f].shape[1] for f in flds])
+        g = vm[name]
+        store[name] = g
+        if any(int(op) >= 27 for op in prog["op"]):          # tangent()/normal()/grad(): only the VM provides them
+            print(f"{name:12s} n={g.size:5d} sum={g.sum():+.15e}  (element helpers: VM only)")
+            continue
         rm = ref.mesh(v, gr)
         h = rm.integral(grade, [tuple(t) for t in prog.tolist()], [fd[f] for f in flds])
         rm.free()
-        g = vm[name]
         assert g.shape == h.shape, (name, g.shape, h.shape)
         err = np.max(np.abs(g - h)) / max(np.max(np.abs(g)), 1e-300)
         print(f"{name:12s} n={g.size:5d} sum={g.sum():+.15e}  VM closure vs harness bytecode: {err:.2e}")
         assert err < 1e-13, name
-        store[name] = g
     for gname, wrt in GRAD_CASES:
         key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
         store[key] = vm[key]

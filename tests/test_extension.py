@@ -105,7 +105,13 @@ def test_closure_translator_reproduces_the_vm(tmp_path):
             vals[w[1]] = [float(w[2]), float(w[3])]
         elif w[0] == "FAIL":
             fails[w[1]] = " ".join(w[2:])
-    assert sorted(progs) == sorted(quantities) == sorted(vals), (sorted(progs), fails)
+    helpers = ["h0", "h1", "h2", "h3"]                    # tangent()/normal()/grad(): translated, but only callable inside an integral
+    assert sorted(progs) == sorted(list(quantities) + helpers) and sorted(vals) == sorted(quantities), (sorted(progs), fails)
+    assert [op for op, a, c in progs["h0"] if op >= 27] == [27, 27] and {op for op, a, c in progs["h1"] if op >= 27} == {28}
+    assert sorted(a for op, a, c in progs["h2"] if op == 29) == [0, 0, 1, 1, 2, 2]                 # d phi / d x_k, twice each
+    assert sorted(a for op, a, c in progs["h3"] if op == 29) == sorted([3 * (1 + c_) + 1 for c_ in range(3)] * 2 + [3 * 1 + 0])
+    for h in helpers:
+        del progs[h]
     for name, prog in progs.items():
         for i in range(2):
             got = _run_program(prog, x[i], quantities[name](i))
@@ -120,7 +126,7 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 34 and evals >= 34 and fallbacks == 2, (stats, err)    # 20 values + 14 gradients; 2 untranslatable
+    assert translated == 49 and evals >= 49 and fallbacks == 1, (stats, err)    # 28 values + 21 gradients; 1 untranslatable
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
     compare(ref[cut:], new[cut:-1], 2e-9)        # finite differences: round-off of f amplified by 1/(2 eps)
