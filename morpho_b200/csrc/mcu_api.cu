@@ -27,6 +27,8 @@ static unsigned *g_hflags = nullptr;   // pinned
 static double *g_hscalar = nullptr;    // pinned
 static std::map<std::string, long> g_opts;
 static void *g_flush_buf = nullptr;
+static double *g_scratch = nullptr;         // grow-only scratch of the element-centric finite-difference maps
+static size_t g_scratch_bytes = 0;
 static size_t g_flush_bytes = 0;
 
 void mcu_set_error(const char *fmt, ...) {
@@ -58,6 +60,20 @@ long mcu_opt(const char *key, long dflt) {
             if (_rc) return _rc;                                        \
         }                                                               \
     } while (0)
+
+double *mcu_scratch(size_t bytes) {
+    if (bytes <= g_scratch_bytes) return g_scratch;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return nullptr;
+    if (bytes > free_b + g_scratch_bytes || bytes > total_b / 2) return nullptr;      // leave room for everything else
+    cudaStreamSynchronize(g_stream);                     // the old buffer may still be in use by queued kernels
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr; g_scratch_bytes = 0;
+    bytes += bytes / 8;
+    if (cudaMalloc((void **) &g_scratch, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_scratch_bytes = bytes;
+    return g_scratch;
+}
 
 extern "C" {
 
@@ -107,6 +123,8 @@ int mcu_init(int device) {
 int mcu_finalize(void) {
     if (!g_inited) return MCU_OK;
     cudaStreamSynchronize(g_stream);
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr; g_scratch_bytes = 0;
     if (g_flush_buf) cudaFree(g_flush_buf);
     g_flush_buf = nullptr; g_flush_bytes = 0;
     cudaFreeHost(g_hflags); cudaFreeHost(g_hscalar);

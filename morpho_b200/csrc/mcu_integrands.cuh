@@ -85,15 +85,17 @@ __device__ __forceinline__ void p1grad_tri(int dim, const double (*x)[3], int nv
 
 // gradsq_evaluategradient3d (functional.c:3584-3620): rows (x_i - x_0)^T, rhs f_i - f_0, solved by
 // LU with partial pivoting in the order LAPACK's dgetf2 + dgetrs use (matrix.c:129-139).
-__device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, const double *vals, int stride, double *out) {
-    // Same operations in the same order as dgetf2 + dgetrs on the 3x3 system; the row exchanges are written as
-    // conditional swaps with constant indices (a run-time pivot index would put a[] and b[] in local memory).
-    double a[9];  // column major Mt: Mt[r + 3 c] = (x_{r+1} - x_0)[c]
+// Split in two so that callers that change only the VALUES (finite differences with respect to a field) factor once.
+struct TetLU { double a[9]; int piv[3]; };
+
+__device__ __forceinline__ void p1grad_tet_factor(const double (*x)[3], TetLU &f) {
+    // Same operations in the same order as dgetf2 on the 3x3 system; the row exchanges are written as
+    // conditional swaps with constant indices (a run-time pivot index would put a[] in local memory).
+    double *a = f.a;  // column major Mt: Mt[r + 3 c] = (x_{r+1} - x_0)[c]
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int c = 0; c < 3; c++) a[r + 3 * c] = x[r + 1][c] - x[0][c];
-    int piv[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         int p = j;
@@ -101,7 +103,7 @@ __device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, cons
 #pragma unroll
         for (int i = j + 1; i < 3; i++)
             if (fabs(a[i + 3 * j]) > big) { big = fabs(a[i + 3 * j]); p = i; }
-        piv[j] = p;
+        f.piv[j] = p;
 #pragma unroll
         for (int i = j + 1; i < 3; i++)
             if (p == i) {
@@ -116,29 +118,54 @@ __device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, cons
 #pragma unroll
             for (int i = j + 1; i < 3; i++) a[i + 3 * c] -= a[i + 3 * j] * a[j + 3 * c];
     }
+}
+
+// dgetrs for one right-hand side: values v0..v3 at the four vertices, out = gradient (3 numbers)
+__device__ __forceinline__ void p1grad_tet_solve(const TetLU &f, double v0, double v1, double v2, double v3, double *out) {
+    const double *a = f.a;
+    double b[3] = {v1 - v0, v2 - v0, v3 - v0};
 #pragma unroll
-    for (int v = 0; v < nvals; v++) {
-        double b[3];
+    for (int j = 0; j < 3; j++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) b[j] = vals[(j + 1) * stride + v] - vals[v];
+        for (int i = j + 1; i < 3; i++)
+            if (f.piv[j] == i) { double tt = b[j]; b[j] = b[i]; b[i] = tt; }
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+    for (int j = 0; j < 3; j++)
 #pragma unroll
-            for (int i = j + 1; i < 3; i++)
-                if (piv[j] == i) { double tt = b[j]; b[j] = b[i]; b[i] = tt; }
+        for (int i = j + 1; i < 3; i++) b[i] -= b[j] * a[i + 3 * j];
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+    for (int j = 2; j >= 0; j--) {
+        b[j] /= a[j + 3 * j];
 #pragma unroll
-            for (int i = j + 1; i < 3; i++) b[i] -= b[j] * a[i + 3 * j];
-#pragma unroll
-        for (int j = 2; j >= 0; j--) {
-            b[j] /= a[j + 3 * j];
-#pragma unroll
-            for (int i = 0; i < j; i++) b[i] -= b[j] * a[i + 3 * j];
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) out[v * 3 + k] = b[k];
+        for (int i = 0; i < j; i++) b[i] -= b[j] * a[i + 3 * j];
     }
+#pragma unroll
+    for (int k = 0; k < 3; k++) out[k] = b[k];
+}
+
+__device__ __forceinline__ void p1grad_tet(const double (*x)[3], int nvals, const double *vals, int stride, double *out) {
+    TetLU f;
+    p1grad_tet_factor(x, f);
+#pragma unroll
+    for (int v = 0; v < nvals; v++) p1grad_tet_solve(f, vals[v], vals[stride + v], vals[2 * stride + v], vals[3 * stride + v], out + v * 3);
+}
+
+// the geometric part of p1grad_tri: the three "perpendiculars" t[j]; grad(value) = sum_j value_j t[j]
+__device__ __forceinline__ void p1grad_tri_factor(int dim, const double (*x)[3], double (*t)[3]) {
+    double s[3][3];
+    for (int k = 0; k < 3; k++) {
+        s[0][k] = x[1][k] - x[0][k];
+        s[1][k] = x[2][k] - x[1][k];
+        s[2][k] = x[0][k] - x[2][k];
+        t[0][k] = t[1][k] = t[2][k] = 0.0;
+    }
+    perpendicular(dim, s[2], s[1], t[0]);
+    perpendicular(dim, s[0], s[2], t[1]);
+    perpendicular(dim, s[1], s[0], t[2]);
+}
+__device__ __forceinline__ void p1grad_tri_apply(int dim, const double (*t)[3], double v0, double v1, double v2, double *out) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) if (k < dim) out[k] = ((0.0 + v0 * t[0][k]) + v1 * t[1][k]) + v2 * t[2][k];
 }
 
 // nematic_bcintf / nematic_bcintfg (functional.c:3818-3834): exact barycentric integrals

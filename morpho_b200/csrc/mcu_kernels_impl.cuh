@@ -279,6 +279,139 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView
     }
 }
 
+// Element-centric form of the two finite-difference maps (p.g > 0).  The vertex-centric kernels above gather and
+// re-evaluate every element once per (vertex, coordinate) from scattered threads; here one thread owns one
+// (element, corner): the nv threads of an element are neighbours in a warp and read the same rows, the central
+// differences go to scratch[(ce * nv + corner) * nc + c], and k_fd_sum adds them per vertex in ascending element id
+// — the order in which functional_numericalgrad / functional_numericalfieldgrad accumulate (functional.c:1142-1162,
+// 1305-1328), so the result is bit-identical to the vertex-centric kernels'.
+template <int F, int SH, bool FIELD>
+__global__ void __launch_bounds__(MCU_BLOCK) k_fd_elem(McuParams p, McuView v, double *scratch) {
+    const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps0 = Shape<SH>::ps(p);
+    const int nc = FIELD ? (p.wrt == 0 ? ps0 : p.psize1) : dim;
+    const long t = (long) blockIdx.x * MCU_BLOCK + threadIdx.x;
+    if (t >= (long) v.n * nv) return;
+    const int ce = (int) (t / nv), corner = (int) (t - (long) ce * nv);
+    const int e = v.eids ? v.eids[ce] : ce;
+    int ids[MCU_MAXNV];
+#pragma unroll
+    for (int j = 0; j < MCU_MAXNV; j++) if (j < nv) ids[j] = v.rix[(size_t) e * nv + j];
+    ElemData d;
+    gather_elem<F>(p, v, ids, d, nv, dim, ps0);
+    double *o = scratch + (size_t) t * nc;
+    if (!FIELD) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (k >= dim) continue;
+            double x0 = elem_getx(d, corner, k);
+            double eps = fdstepsize(x0);
+            elem_setx(d, corner, k, x0 + eps);
+            double fp = eval_integrand<F>(p, d, nv, dim, ps0);
+            elem_setx(d, corner, k, x0 - eps);
+            double fm = eval_integrand<F>(p, d, nv, dim, ps0);
+            elem_setx(d, corner, k, x0);
+            o[k] = (fp - fm) / (2 * eps);
+        }
+    } else if (SH) {
+#pragma unroll
+        for (int i = 0; i < MCU_MAXPSIZE; i++) {
+            if (i >= nc) continue;
+            double f0 = (p.wrt == 0) ? elem_getq(d, corner, i) : elem_getphi(d, corner);
+            double eps = fdstepsize(f0);
+            if (p.wrt == 0) elem_setq(d, corner, i, f0 + eps); else elem_setphi(d, corner, f0 + eps);
+            double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+            if (p.wrt == 0) elem_setq(d, corner, i, f0 - eps); else elem_setphi(d, corner, f0 - eps);
+            double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+            if (p.wrt == 0) elem_setq(d, corner, i, f0); else elem_setphi(d, corner, f0);
+            o[i] = (fr - fl) / (2 * eps);
+        }
+    } else {
+        for (int i = 0; i < nc; i++) {
+            double *slot = (p.wrt == 0 ? &d.q[corner][i] : &d.phi[corner]);
+            double f0 = *slot;
+            double eps = fdstepsize(f0);
+            *slot = f0 + eps;
+            double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+            *slot = f0 - eps;
+            double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+            *slot = f0;
+            o[i] = (fr - fl) / (2 * eps);
+        }
+    }
+}
+
+// GradSq.fieldgradient, specialised: a perturbation of one field value changes only that component's gradient, and
+// the geometry (LU factors of the tetrahedron / perpendiculars of the triangle, element size) not at all.  The
+// arithmetic of every number that IS recomputed is the one gradsq_integrand performs (same helper functions, same
+// order), so the differences are bit-identical to re-evaluating the whole integrand twice per degree of freedom.
+template <int NV, int PS>
+__global__ void __launch_bounds__(MCU_BLOCK) k_gradsq_fd_elem(McuParams p, McuView v, double *scratch) {
+    const long t = (long) blockIdx.x * MCU_BLOCK + threadIdx.x;
+    if (t >= (long) v.n * NV) return;
+    const int ce = (int) (t / NV), corner = (int) (t - (long) ce * NV);
+    const int e = v.eids ? v.eids[ce] : ce;
+    double x[MCU_MAXNV][3], q[NV][PS];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int id = v.rix[(size_t) e * NV + j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) x[j][k] = v.vert[(size_t) id * 3 + k];
+#pragma unroll
+        for (int i = 0; i < PS; i++) q[j][i] = v.f0[(size_t) id * PS + i];
+    }
+    const double size = elem_size(NV - 1, x);
+    TetLU lu;
+    double tt[3][3];
+    if (NV == 4) p1grad_tet_factor(x, lu); else p1grad_tri_factor(3, x, tt);
+    double grad[PS * 3];
+#pragma unroll
+    for (int i = 0; i < PS; i++) {
+        if (NV == 4) p1grad_tet_solve(lu, q[0][i], q[1][i], q[2][i], q[3 % NV][i], grad + 3 * i);
+        else p1grad_tri_apply(3, tt, q[0][i], q[1][i], q[2][i], grad + 3 * i);
+    }
+    double *o = scratch + (size_t) t * PS;
+#pragma unroll
+    for (int i = 0; i < PS; i++) {
+        double f0 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) if (j == corner) f0 = q[j][i];
+        const double eps = fdstepsize(f0);
+        double f[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const double val = s == 0 ? f0 + eps : f0 - eps;
+            double w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = (j < NV) ? (j == corner ? val : q[j % NV][i]) : 0.0;
+            double g3[3], tmp[PS * 3];
+            if (NV == 4) p1grad_tet_solve(lu, w[0], w[1], w[2], w[3], g3); else p1grad_tri_apply(3, tt, w[0], w[1], w[2], g3);
+#pragma unroll
+            for (int c = 0; c < PS * 3; c++) tmp[c] = (c / 3 == i) ? g3[c % 3] : grad[c];
+            const double nrm = vnorm(PS * 3, tmp);
+            f[s] = nrm * nrm * size;
+        }
+        o[i] = (f[0] - f[1]) / (2 * eps);
+    }
+}
+
+static __global__ void __launch_bounds__(MCU_BLOCK) k_fd_sum(int nvtx, int nv, int nc, McuView v, const double *__restrict__ scratch, double *__restrict__ out) {
+    int vtx = blockIdx.x * MCU_BLOCK + threadIdx.x;
+    if (vtx >= nvtx) return;
+    double acc[MCU_MAXPSIZE];
+#pragma unroll
+    for (int c = 0; c < MCU_MAXPSIZE; c++) acc[c] = 0.0;
+    for (int q = v.tptr[vtx]; q < v.tptr[vtx + 1]; q++) {
+        const int ce = v.tidx[q], e = v.eids ? v.eids[ce] : ce;
+        int corner = 0;
+        for (int j = 0; j < nv; j++) if (v.rix[(size_t) e * nv + j] == vtx) corner = j;
+        const double *src = scratch + ((size_t) ce * nv + corner) * nc;
+#pragma unroll
+        for (int c = 0; c < MCU_MAXPSIZE; c++) if (c < nc) acc[c] = acc[c] + src[c];
+    }
+#pragma unroll
+    for (int c = 0; c < MCU_MAXPSIZE; c++) if (c < nc) out[(size_t) vtx * nc + c] = acc[c];
+}
+
 // ---------------------------------------------------------------------------------
 // host-side launch helpers shared by both translation units
 // ---------------------------------------------------------------------------------
@@ -347,8 +480,46 @@ static cudaError_t run_grad_gather(const McuParams &p, const McuView &v, double 
     return cudaGetLastError();
 }
 
+double *mcu_scratch(size_t bytes);      // grow-only device buffer (mcu_api.cu); nullptr if it cannot be had
+long mcu_opt(const char *key, long dflt);
+
+// element-centric when the scratch fits (option fd_elementwise, default 1), else the vertex-centric kernels
+template <int F, bool FIELD>
+static bool run_fd_elementwise(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
+    // measured (scripts/field_bench.py, scripts/tet_bench.py): the element-centric form wins for field gradients
+    // and loses a few per cent for position gradients
+    const long choice = mcu_opt("fd_elementwise", -1);          // -1: the default per kind, 0 / 1: forced
+    if (p.g <= 0 || !(choice < 0 ? FIELD : choice != 0)) return false;
+    const int nc = FIELD ? (p.wrt == 0 ? p.psize0 : p.psize1) : p.dim;
+    if (nc > MCU_MAXPSIZE) return false;
+    const long nt = (long) v.n * p.nvper;
+    double *scratch = mcu_scratch(sizeof(double) * (size_t) std::max(nt, 1L) * nc);
+    if (!scratch) return false;
+    const int sh = mcu_shape_of<F>(p);
+    bool done = false;
+    if constexpr (F == MCU_F_GRADSQ && FIELD) {
+        if (nt > 0 && p.wrt == 0 && p.dim == 3 && mcu_opt("gradsq_fast_fieldgradient", 1)) {
+            const unsigned gb = (unsigned) ((nt + MCU_BLOCK - 1) / MCU_BLOCK);
+#define G_(NV, PS) if (!done && p.nvper == NV && p.psize0 == PS) { k_gradsq_fd_elem<NV, PS><<<gb, MCU_BLOCK, 0, st>>>(p, v, scratch); done = true; }
+            G_(3, 1) G_(3, 3) G_(3, 5) G_(4, 1) G_(4, 3) G_(4, 5)
+#undef G_
+            if (done) g_mcu_launches += 1;
+        }
+    }
+    if (nt > 0 && !done) {
+#define L_(S) k_fd_elem<F, S, FIELD><<<(unsigned) ((nt + MCU_BLOCK - 1) / MCU_BLOCK), MCU_BLOCK, 0, st>>>(p, v, scratch)
+        MCU_SHAPE_SWITCH(F, sh, L_);
+#undef L_
+        g_mcu_launches += 1;
+    }
+    k_fd_sum<<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p.nv, p.nvper, nc, v, scratch, d_out);
+    g_mcu_launches += 1;
+    return true;
+}
+
 template <int F>
 static cudaError_t run_fd_grad(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
+    if (run_fd_elementwise<F, false>(p, v, d_out, st)) return cudaGetLastError();
     const int sh = mcu_shape_of<F>(p);
 #define L_(S) k_fd_grad<F, S><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out)
     MCU_SHAPE_SWITCH(F, sh, L_);
@@ -359,6 +530,7 @@ static cudaError_t run_fd_grad(const McuParams &p, const McuView &v, double *d_o
 
 template <int F>
 static cudaError_t run_fd_fieldgrad(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
+    if (run_fd_elementwise<F, true>(p, v, d_out, st)) return cudaGetLastError();
     const int sh = mcu_shape_of<F>(p);
 #define L_(S) k_fd_fieldgrad<F, S><<<(p.nv + MCU_BLOCK - 1) / MCU_BLOCK, MCU_BLOCK, 0, st>>>(p, v, d_out)
     MCU_SHAPE_SWITCH(F, sh, L_);

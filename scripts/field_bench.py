@@ -8,6 +8,8 @@ import morpho_b200 as mb
 from morpho_b200 import _lib, meshgen as mg
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 816
 mb.init(0); L = mb.lib()
+if len(sys.argv) > 2:
+    mb.set_option("fd_elementwise", int(sys.argv[2]))     # 0: vertex-centric finite-difference kernels
 v, faces, bnd = mg.disk(n, dim=3)
 rng = np.random.Generator(np.random.PCG64(12345))
 th = 0.3 * rng.uniform(-1, 1, size=v.shape[0]) + 0.5 * v[:, 0]
