@@ -35,7 +35,9 @@ struct McuPatchRun {      // 8 bytes
 };
 
 // What the producer warps read per patch, addressed by the patch index alone (one latency, prefetchable):
-#define MCU_PATCH_DESC_RUNS 64
+#ifndef MCU_PATCH_DESC_RUNS
+#define MCU_PATCH_DESC_RUNS 64        // = 32 lanes x producer warps
+#endif
 struct McuPatchDesc {     // 544 bytes
     McuPatchHeader h;
     McuPatchRun runs[MCU_PATCH_DESC_RUNS];   // the first runs of the patch; the rest (rare) at runs[h.run_off + 64 ..]
