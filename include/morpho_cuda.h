@@ -176,6 +176,13 @@ int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int 
 int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                           mcu_selection *sel, int wrt, double *host_out);
 
+/* ---- ScalarPotential (functional.c:2255-2372): a function of the position evaluated at every (selected) vertex, given
+ *      as a postfix program over MCU_X_POS (no field / element ops).  nprog programs are concatenated in progs, program k
+ *      has nops[k] ops.  MCU_TOTAL (1 double) and MCU_INTEGRAND (nv doubles): nprog = 1.  MCU_GRADIENT (nv * dim
+ *      doubles): nprog = dim gives the components of the gradient function, nprog = 1 takes central differences of the
+ *      potential like functional_mapnumericalgradient does when no gradient function was supplied. ---- */
+int mcu_pointwise(mcu_mesh *m, int nprog, const int *nops, const mcu_expr_op *progs, mcu_selection *sel, int mode, double *host_out);
+
 /* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.
  *      kind 0: Coulomb f=1/r, f'=-1/r^2 (examples/thomson/thomson.morpho:26).
  *      mode MCU_TOTAL / MCU_INTEGRAND (n doubles) / MCU_GRADIENT (n*dim doubles). ---- */

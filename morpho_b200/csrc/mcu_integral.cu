@@ -61,10 +61,11 @@ struct MiView {
     int ngrad, gsrc[MI_MAXG], gslot[MI_MAXG];  // gradient of component gsrc[i] in slots gslot[i] .. +2
 };
 
-__device__ __forceinline__ double mi_eval(const MiView &v, const double *x, const double *q) {
+// the postfix machine: ops c_prog[off .. off + len)
+__device__ __forceinline__ double mi_run(int off, int len, const double *x, const double *q) {
     double st[MI_STACK];
     int sp = 0;
-    for (int i = 0; i < v.nops; i++) {
+    for (int i = off; i < off + len; i++) {
         const mcu_expr_op op = c_prog[i];
         switch (op.op) {
             case MCU_X_CONST: st[sp++] = op.c; break;
@@ -99,6 +100,7 @@ __device__ __forceinline__ double mi_eval(const MiView &v, const double *x, cons
     }
     return sp > 0 ? st[sp - 1] : 0.0;
 }
+__device__ __forceinline__ double mi_eval(const MiView &v, const double *x, const double *q) { return mi_run(0, v.nops, x, q); }
 
 // integrand at the point with barycentric coordinates lam[0..nv) of the ROOT element
 template <int NV>
@@ -415,6 +417,116 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
     if (cudaMemcpyToSymbolAsync(c_prog, prog, sizeof(mcu_expr_op) * nops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) return MCU_ERR_CUDA;
     return MCU_OK;
+}
+
+// ---- ScalarPotential (functional.c:2255-2372): a function of the position evaluated at every vertex ----
+struct PwView {
+    int dim, n, nprog;
+    const double *vert;
+    const int *ids;                            // selected vertices or nullptr
+    int off[3], len[3];                        // the programs inside c_prog
+};
+
+__global__ void __launch_bounds__(256) k_pw_values(PwView v, double *out) {
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= v.n) return;
+    const int id = v.ids ? v.ids[c] : c;
+    double x[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < v.dim; k++) x[k] = v.vert[(size_t) id * v.dim + k];
+    out[id] = mi_run(v.off[0], v.len[0], x, x);
+}
+
+// gradient: the gradient function's components if given (scalarpotential_gradient adds the returned Matrix to the
+// zeroed column), else central differences of the potential (functional_numericalgrad with the vertex as element)
+__global__ void __launch_bounds__(256) k_pw_grad(PwView v, double *out) {
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= v.n) return;
+    const int id = v.ids ? v.ids[c] : c;
+    double x[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < v.dim; k++) x[k] = v.vert[(size_t) id * v.dim + k];
+    for (int k = 0; k < v.dim; k++) {
+        double g;
+        if (v.nprog > 1) g = 0.0 + 1.0 * mi_run(v.off[k], v.len[k], x, x);
+        else {
+            const double x0 = x[k], eps = fdstepsize(x0);
+            x[k] = x0 + eps;
+            const double fp = mi_run(v.off[0], v.len[0], x, x);
+            x[k] = x0 - eps;
+            const double fm = mi_run(v.off[0], v.len[0], x, x);
+            x[k] = x0;
+            g = 0.0 + (fp - fm) / (2 * eps);
+        }
+        out[(size_t) id * v.dim + k] = g;
+    }
+}
+
+static int validate_program(const mcu_expr_op *prog, int nops, int dim, int nq, bool element_ops) {
+    int depth = 0;
+    for (int i = 0; i < nops; i++) {
+        const mcu_expr_op &op = prog[i];
+        if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
+            if ((op.op == MCU_X_POS && (op.a < 0 || op.a >= dim)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= nq))) { mcu_set_error("operand out of range at op %d", i); return MCU_ERR_ARGS; }
+            depth++;
+        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2) { if (depth < 2) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
+        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) { if (depth < 1) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        else if (element_ops && op.op >= MCU_X_TANGENT && op.op <= MCU_X_GRADQ) depth++;
+        else { mcu_set_error("op %d not allowed here", op.op); return MCU_ERR_ARGS; }
+        if (depth > MI_STACK) { mcu_set_error("expression stack too deep"); return MCU_ERR_UNSUPPORTED; }
+    }
+    if (depth != 1) { mcu_set_error("program leaves %d values", depth); return MCU_ERR_ARGS; }
+    return MCU_OK;
+}
+
+extern "C" int mcu_pointwise(mcu_mesh *m, int nprog, const int *nops, const mcu_expr_op *progs, mcu_selection *sel, int mode, double *host_out) {
+    if (!m || !nops || !progs || !host_out || nprog < 1 || nprog > 3) { mcu_set_error("bad pointwise arguments"); return MCU_ERR_ARGS; }
+    if (mode != MCU_TOTAL && mode != MCU_INTEGRAND && mode != MCU_GRADIENT) { mcu_set_error("bad pointwise mode"); return MCU_ERR_ARGS; }
+    if ((mode != MCU_GRADIENT && nprog != 1) || (mode == MCU_GRADIENT && nprog != 1 && nprog != m->dim)) { mcu_set_error("pointwise: wrong number of programs"); return MCU_ERR_ARGS; }
+    if (sel && (sel->m != m || sel->g != 0)) { mcu_set_error("selection does not belong to this mesh / grade 0"); return MCU_ERR_ARGS; }
+    PwView v;
+    memset(&v, 0, sizeof(v));
+    int total_ops = 0;
+    for (int k = 0; k < nprog; k++) {
+        if (nops[k] < 1 || total_ops + nops[k] > MI_MAXOPS) { mcu_set_error("pointwise programs too long"); return MCU_ERR_UNSUPPORTED; }
+        int rc = validate_program(progs + total_ops, nops[k], m->dim, 0, false);
+        if (rc) return rc;
+        v.off[k] = total_ops; v.len[k] = nops[k];
+        total_ops += nops[k];
+    }
+    cudaStream_t st = mcu_stream();
+    if (sel) { int rs = mcu_ensure_selection(sel); if (rs) return rs; }
+    v.dim = m->dim; v.nprog = nprog; v.vert = m->d_vert;
+    v.ids = sel ? sel->d_eids : nullptr;
+    v.n = sel ? (int) sel->ids.size() : m->nv;
+    if (cudaMemcpyToSymbolAsync(c_prog, progs, sizeof(mcu_expr_op) * total_ops, 0, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) return MCU_ERR_CUDA;
+    const size_t nout = mode == MCU_GRADIENT ? (size_t) m->nv * m->dim : (size_t) m->nv;
+    double *d_out = nullptr, *d_tot = nullptr;
+    CompSum *d_part = nullptr;
+    int rc = MCU_OK;
+    if (cudaMalloc((void **) &d_out, sizeof(double) * std::max<size_t>(nout, 1)) != cudaSuccess) return MCU_ERR_ALLOC;
+    cudaMemsetAsync(d_out, 0, sizeof(double) * std::max<size_t>(nout, 1), st);
+    if (v.n > 0) {
+        if (mode == MCU_GRADIENT) k_pw_grad<<<(v.n + 255) / 256, 256, 0, st>>>(v, d_out);
+        else k_pw_values<<<(v.n + 255) / 256, 256, 0, st>>>(v, d_out);
+        g_mcu_launches += 1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mode == MCU_TOTAL) {
+        int rb = std::max(1, std::min(1024, (m->nv + 255) / 256));
+        if (cudaMalloc((void **) &d_part, sizeof(CompSum) * rb) != cudaSuccess || cudaMalloc((void **) &d_tot, 8) != cudaSuccess) rc = MCU_ERR_ALLOC;
+        else {
+            k_isum<<<rb, 256, 0, st>>>(d_out, m->nv, d_part);
+            k_isum_finish<<<1, 256, 0, st>>>(d_part, rb, d_tot);
+            g_mcu_launches += 2;
+            e = cudaMemcpyAsync(host_out, d_tot, 8, cudaMemcpyDeviceToHost, st);
+        }
+    } else if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { mcu_set_error("pointwise evaluation failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
+    cudaFree(d_out);
+    if (d_part) cudaFree(d_part);
+    if (d_tot) cudaFree(d_tot);
+    return rc;
 }
 
 /* Gradient of the integral by central differences, like the reference (LineIntegral/AreaIntegral gradient and

@@ -232,6 +232,21 @@ static bool mt_call(mt_ctx *c, const mt_sym *callee, const mt_sym *args, int nar
     if (MORPHO_ISFUNCTION(fn) || MORPHO_ISCLOSURE(fn)) return mt_interp(c, fn, args, nargs, out);
     const char *name = mt_builtinname(fn);
     if (!name) return mt_fail(c, "call of an unknown builtin");
+    /* List(a, b, ...) of numbers and Matrix(list) / Matrix(n): small constant-shape vectors built inside the closure */
+    if (!strcmp(name, "List") && nargs >= 1 && nargs <= MT_MAXCOMP) {
+        *out = mt_none(); out->kind = MT_VEC; out->nrows = nargs; out->ncols = 1;
+        for (int i = 0; i < nargs; i++) { if (args[i].kind != MT_NUM) return mt_fail(c, "List of non-numbers"); out->node[i] = args[i].node[0]; }
+        return true;
+    }
+    if (!strcmp(name, "Matrix") && nargs == 1) {
+        if (args[0].kind == MT_VEC && args[0].ncols == 1) { *out = args[0]; out->field = -1; return true; }
+        if (args[0].kind == MT_NUM && mt_isint(c, args[0].node[0]) && c->nodes[args[0].node[0]].a >= 1 && c->nodes[args[0].node[0]].a <= MT_MAXCOMP) {
+            *out = mt_none(); out->kind = MT_VEC; out->nrows = c->nodes[args[0].node[0]].a; out->ncols = 1;
+            for (int i = 0; i < out->nrows; i++) out->node[i] = mt_constf(c, 0.0);
+            return true;
+        }
+        return mt_fail(c, "unsupported Matrix constructor");
+    }
     /* element helpers (functional.c:4396-4745): constants of the element, leaves of the expression */
     if (nargs == 0 && (!strcmp(name, "tangent") || !strcmp(name, "normal"))) {
         *out = mt_none(); out->kind = MT_VEC; out->nrows = c->dim; out->ncols = 1;
@@ -425,6 +440,34 @@ static bool mc_translate_integrand(vm *v, value fn, int dim, int nfields, const 
     ok = ok && mt_interp(c, fn, args, nfields + 1, &ret);
     if (ok && ret.kind != MT_NUM) ok = mt_fail(c, "integrand does not return a number");
     ok = ok && mt_emit(c, ret.node[0], prog, nops, cap);
+    *why = c->why ? c->why : "";
+    free(c);
+    return ok;
+}
+
+/* ScalarPotential: fn(x, y[, z]) of the coordinates (scalarpotential_integrand, functional.c:2266-2280).  A function
+ * that returns a number gives one program; one that returns a Matrix of dim entries (the gradient function,
+ * scalarpotential_gradient 2283-2303) gives dim programs, concatenated in prog with their lengths in nops[]. */
+static bool mc_translate_pointfn(vm *v, value fn, int dim, mcu_expr_op *prog, int cap, int *nops, int *nprog, const char **why) {
+    mt_ctx *c = (mt_ctx *) calloc(1, sizeof(mt_ctx));
+    if (!c) { *why = "allocation"; return false; }
+    c->v = v;
+    c->dim = dim;
+    mt_sym args[3], ret;
+    for (int i = 0; i < dim && i < 3; i++) args[i] = mt_num(mt_new(c, MCU_X_POS, i, 0, 0.0, 0));
+    bool ok = dim >= 1 && dim <= 3 && mt_interp(c, fn, args, dim, &ret);
+    *nprog = 0;
+    int total = 0;
+    if (ok) {
+        const int n = ret.kind == MT_NUM ? 1 : ret.nrows * ret.ncols;
+        if (ret.kind == MT_VEC && n != dim) ok = mt_fail(c, "gradient function returns a Matrix of the wrong size");
+        for (int k = 0; k < n && ok; k++) {
+            int len = 0;
+            ok = mt_emit(c, ret.node[k], prog + total, &len, cap - total);
+            nops[k] = len; total += len;
+        }
+        if (ok) *nprog = n;
+    }
     *why = c->why ? c->why : "";
     free(c);
     return ok;

@@ -493,6 +493,71 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     return false;
 }
 
+/* ScalarPotential total / integrand / gradient (functional.c:2255-2372): the potential (and, if given, its gradient
+ * function) is translated like an integrand; without a gradient function the device takes the same central
+ * differences as functional_mapnumericalgradient. */
+static bool mc_eval_scalarpotential(vm *v, int nargs, value *args, int mode, value *out) {
+    functional_mapinfo info;
+    *out = MORPHO_NIL;
+    if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
+    if (!functional_validateargs(v, nargs, args, &info)) return true;
+    objectinstance *self = MORPHO_GETINSTANCE(MORPHO_SELF(args));
+    if (info.field || (info.sel && info.sel->mode != SELECT_SOME) || mesh_has_symmetries(info.mesh, 0)) return false;
+    value fn = MORPHO_NIL, gfn = MORPHO_NIL;
+    if (!prop(self, SCALARPOTENTIAL_FUNCTION_PROPERTY, &fn)) return false;
+    bool hasgrad = prop(self, SCALARPOTENTIAL_GRADFUNCTION_PROPERTY, &gfn) && !MORPHO_ISNIL(gfn);
+    mc_mirror *mr = mirror_get(info.mesh, 0);
+    if (!mr) return false;
+    mcu_expr_op prog[MC_MAXPROG];
+    int nops[3] = {0, 0, 0}, nprog = 0;
+    const char *why = "";
+    if (!mc_translate_pointfn(v, (mode == MCU_GRADIENT && hasgrad) ? gfn : fn, mr->dim, prog, MC_MAXPROG, nops, &nprog, &why) ||
+        nprog != ((mode == MCU_GRADIENT && hasgrad) ? mr->dim : 1)) {
+        mc_log("potential not translated:", why);
+        return false;
+    }
+    mc_stat_translated++;
+    mcu_selection *sel = NULL;
+    if (info.sel) {
+        int *ids, n = selection_ids(info.sel, 0, &ids);
+        if (n < 0) return false;
+        sel = mcu_selection_create(mr->m, 0, n, ids);
+        free(ids);
+        if (!sel) return false;
+    }
+    int rc;
+    double total = 0.0;
+    objectmatrix *new = NULL;
+    if (mode == MCU_TOTAL) rc = mcu_pointwise(mr->m, nprog, nops, prog, sel, MCU_TOTAL, &total);
+    else {
+        new = (mode == MCU_INTEGRAND) ? matrix_new(1, mr->nv, false) : matrix_new(mr->dim, mr->nv, false);
+        if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
+        else rc = mcu_pointwise(mr->m, nprog, nops, prog, sel, mode, new->elements);
+    }
+    if (sel) mcu_selection_destroy(sel);
+    if (rc == MCU_OK) {
+        mc_stat_evals++;
+        if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
+        else { *out = MORPHO_OBJECT(new); morpho_bindobjects(v, 1, out); }
+        return true;
+    }
+    if (new) object_free((object *) new);
+    if (rc == -1) return true;
+    mc_log("potential not accelerated:", mcu_last_error());
+    return false;
+}
+#define MC_SVENEER(meth, MODE) \
+    static builtinfunction orig_ScalarPotential_##meth = NULL; \
+    static value mc_ScalarPotential_##meth(vm *v, int nargs, value *args) { \
+        value out; \
+        if (mc_eval_scalarpotential(v, nargs, args, MODE, &out)) return out; \
+        mc_stat_fallbacks++; \
+        return orig_ScalarPotential_##meth(v, nargs, args); \
+    }
+MC_SVENEER(total, MCU_TOTAL)
+MC_SVENEER(integrand, MCU_INTEGRAND)
+MC_SVENEER(gradient, MCU_GRADIENT)
+
 #define MC_IVENEER(cls, GRADE, meth, MODE) \
     static builtinfunction orig_##cls##_##meth = NULL; \
     static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
@@ -691,6 +756,7 @@ void morphocuda_initialize(void) {
     PATCH(Nematic, total); PATCH(Nematic, integrand); PATCH(Nematic, gradient); PATCH(Nematic, fieldgradient);
     PATCH(NematicElectric, total); PATCH(NematicElectric, integrand); PATCH(NematicElectric, gradient); PATCH(NematicElectric, fieldgradient);
     PATCH(LineCurvatureSq, total); PATCH(LineCurvatureSq, integrand); PATCH(LineCurvatureSq, gradient);
+    PATCH(ScalarPotential, total); PATCH(ScalarPotential, integrand); PATCH(ScalarPotential, gradient);
     PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
     PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
 

@@ -20,7 +20,7 @@ from ._lib import (MCU_FIELDGRADIENT, MCU_GRADIENT, MCU_INTEGRAND, MCU_TOTAL, FU
 from .geometry import Field, Mesh, Selection
 
 __all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq",
-           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral"]
+           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral", "ScalarPotential"]
 
 
 class Functional:
@@ -281,3 +281,37 @@ class LineIntegral(_Integral):
 
 class AreaIntegral(_Integral):
     grade = 2
+
+
+class ScalarPotential:
+    """ScalarPotential(f[, gradf]) (functional.c:2255-2372): ``f(x, y, z)`` summed over the (selected) vertices; the
+    gradient comes from ``gradf(x, y, z)`` (a sequence of ``dim`` expressions) if given, else from central differences
+    of ``f`` exactly like the reference.  Both callables use the operators of :mod:`morpho_b200.integrand`."""
+
+    def __init__(self, fn, gradfn=None):
+        self.fn, self.gradfn = fn, gradfn
+
+    def _eval(self, mode, args):
+        from .integrand import trace_point
+        mesh, sel, _ = Functional._args(args)
+        use_grad = mode == MCU_GRADIENT and self.gradfn is not None
+        progs = trace_point(self.gradfn if use_grad else self.fn, mesh.dim)
+        if len(progs) != (mesh.dim if use_grad else 1):
+            raise MorphoError(_lib.MCU_ERR_ARGS, "SclrPtFnCllbl", "ScalarPotential function returns the wrong number of values")
+        allops = np.concatenate(progs)
+        nops = np.array([len(p) for p in progs], dtype=np.int32)
+        n = {MCU_TOTAL: 1, MCU_INTEGRAND: mesh.nv, MCU_GRADIENT: mesh.nv * mesh.dim}[mode]
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        hsel = sel._handle(0) if sel is not None else None
+        check(lib().mcu_pointwise(mesh._h, len(progs), nops.ctypes.data, allops.ctypes.data, hsel, mode, out.ctypes.data))
+        return out[:n]
+
+    def total(self, *args):
+        return float(self._eval(MCU_TOTAL, args)[0])
+
+    def integrand(self, *args):
+        return self._eval(MCU_INTEGRAND, args)
+
+    def gradient(self, *args):
+        mesh, _, _ = Functional._args(args)
+        return self._eval(MCU_GRADIENT, args).reshape(mesh.nv, mesh.dim)

@@ -19,7 +19,7 @@ BINARY = ("add", "sub", "mul", "div", "pow", "atan2")
 OP_DTYPE = np.dtype([("op", "<i4"), ("a", "<i4"), ("c", "<f8")])
 
 __all__ = ["Expr", "trace", "sqrt", "sin", "cos", "exp", "log", "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh",
-           "tanh", "floor", "ceil", "log10", "tangent", "normal", "grad", "OPS", "OP_DTYPE"]
+           "tanh", "floor", "ceil", "log10", "tangent", "normal", "grad", "trace_point", "OPS", "OP_DTYPE"]
 
 
 class Expr:
@@ -127,3 +127,17 @@ def trace(fn, dim, field_sizes):
     for i, t in enumerate(out.prog):
         prog[i] = t
     return prog
+
+
+def trace_point(fn, dim):
+    """Programs of ``fn(x, y[, z])`` (ScalarPotential): one if it returns a number, ``dim`` if it returns a sequence."""
+    out = fn(*(Expr([(OPS["pos"], k, 0.0)]) for k in range(dim)))
+    outs = list(out) if isinstance(out, (tuple, list)) else [out]
+    progs = []
+    for o in outs:
+        e = Expr.lift(o)
+        prog = np.zeros(len(e.prog), dtype=OP_DTYPE)
+        for i, t in enumerate(e.prog):
+            prog[i] = t
+        progs.append(prog)
+    return progs

@@ -70,3 +70,13 @@ GRAD_CASES = [("line_poly", -1), ("line_osc", -1), ("line_field", -1), ("line_fi
               ("area_quad", -1), ("area_osc", -1), ("area_field", -1), ("area_field", 0), ("area_field", 1), ("area_sel", 0),
               ("line_tangent", -1), ("area_anchor", -1), ("area_anchor", 0), ("area_gradsq", -1), ("area_gradsq", 0),
               ("area_gradvec", 0)]
+
+
+# ScalarPotential: name, mesh, f, gradf or None, Morpho sources, selected vertex ids or None
+POT_CASES = [
+    ("pot_grad", "sphere", lambda x, y, z: x ** 2 + y * z - cos(2.5 * z), lambda x, y, z: (2 * x, z, y + 2.5 * sin(2.5 * z)),
+     "fn (x,y,z) x^2+y*z-cos(2.5*z)", "fn (x,y,z) Matrix([2*x, z, y+2.5*sin(2.5*z)])", None),
+    ("pot_fd", "sphere", lambda x, y, z: exp(-x * x) * y + sqrt(1.5 + z), None, "fn (x,y,z) exp(-x*x)*y+sqrt(1.5+z)", None, None),
+    ("pot_sel", "loop", lambda x, y, z: sin(3 * x) * y - z, None, "fn (x,y,z) sin(3*x)*y-z", None, [0, 2, 3, 10, 23]),
+    ("pot_2d", "disk2d", lambda x, y: x * y + exp(x), lambda x, y: (y + exp(x), x), "fn (x,y) x*y+exp(x)", "fn (x,y) Matrix([y+exp(x), x])", None),
+]

@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 from morpho_b200 import meshgen as mg  # noqa: E402
 from morpho_b200.integrand import trace  # noqa: E402
 from oracle.oracle import Reference  # noqa: E402
-from tests.golden.integral_cases import CASES, FIELD_SRC, GRAD_CASES, fields_for, meshes  # noqa: E402
+from tests.golden.integral_cases import CASES, FIELD_SRC, GRAD_CASES, POT_CASES, fields_for, meshes  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref")
 
@@ -62,6 +62,23 @@ def vm_integrands(tmp, ms):
         else:
             src.append(f"var g_{key} = {cls}({closure}{fargs}).fieldgradient({flds[wrt]}_{mesh}, m_{mesh}{selarg})")
             src.append(f'for (x in g_{key}) {{ if (ismatrix(x)) {{ for (y in x) print y.format("%.17g") }} else print x.format("%.17g") }}')
+    for name, mesh, _, gradf, fsrc, gsrc, sel in POT_CASES:
+        src.append(f"var p_{name} = ScalarPotential({fsrc}{', ' + gsrc if gsrc else ''})")
+        selarg = ""
+        if sel is not None:
+            src.append(f"var s_{name} = Selection(m_{mesh})")
+            for i in sel:
+                src.append(f"s_{name}[0,{i}] = true")
+            selarg = f", s_{name}"
+        src.append(f'print "@{name}__total"')
+        src.append(f'print p_{name}.total(m_{mesh}{selarg}).format("%.17g")')
+        src.append(f'print "@{name}__integrand"')
+        src.append(f"var pi_{name} = p_{name}.integrand(m_{mesh}{selarg})")
+        src.append(f'for (i in 0...pi_{name}.dimensions()[1]) print pi_{name}[0,i].format("%.17g")')
+        src.append(f'print "@{name}__gradient"')
+        src.append(f"var pg_{name} = p_{name}.gradient(m_{mesh}{selarg})")
+        src.append(f"var pd_{name} = pg_{name}.dimensions()")
+        src.append(f'for (i in 0...pd_{name}[1]) for (k in 0...pd_{name}[0]) print pg_{name}[k,i].format("%.17g")')
     path = os.path.join(tmp, "integrals.morpho")
     open(path, "w").write("\n".join(src) + "\n")
     env = dict(os.environ, HOME=os.path.join(REF, "home"), OPENBLAS_NUM_THREADS="1")
@@ -104,6 +121,10 @@ def main():
         key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
         store[key] = vm[key]
         print(f"{key:28s} n={vm[key].size:5d} |g|={np.linalg.norm(vm[key]):.15e}")
+    for name, *_ in POT_CASES:
+        for what in ("total", "integrand", "gradient"):
+            store[f"{name}__{what}"] = vm[f"{name}__{what}"]
+        print(f"{name:12s} total={vm[name + '__total'][0]:+.15e} |g|={np.linalg.norm(vm[name + '__gradient']):.6e}")
     np.savez_compressed(os.path.join(HERE, "integrals.npz"), **store)
     print("wrote integrals.npz")
 

@@ -94,7 +94,8 @@ def test_closure_translator_reproduces_the_vm(tmp_path):
     qv = [[0.2, -1.3, 0.8], [1.5, 0.1, -0.6]]
     tm = [[1.0, -0.3, 0.2, 0.7], [0.4, 0.9, -1.1, 0.05]]           # column-major 2x2
     quantities = {"f0": lambda i: [], "f1": lambda i: [p[i]] + qv[i], "f2": lambda i: qv[i], "f3": lambda i: qv[i],
-                  "f4": lambda i: [], "f5": lambda i: tm[i], "f6": lambda i: [], "f7": lambda i: [], "f8": lambda i: [p[i]]}
+                  "f4": lambda i: [], "f5": lambda i: tm[i], "f6": lambda i: [], "f7": lambda i: [], "f8": lambda i: [p[i]],
+                  "f9": lambda i: []}
     progs, vals, fails = {}, {}, {}
     for line in out:
         w = line.split()
@@ -116,7 +117,7 @@ def test_closure_translator_reproduces_the_vm(tmp_path):
         for i in range(2):
             got = _run_program(prog, x[i], quantities[name](i))
             assert abs(got - vals[name][i]) <= 4e-15 * max(1.0, abs(vals[name][i])), (name, i, got, vals[name][i])
-    assert sorted(fails) == ["g0", "g1", "g2", "g3", "g4", "g5", "g6"], fails      # left to the reference builtin
+    assert sorted(fails) == ["g0", "g1", "g2", "g3", "g4", "g5"], fails      # left to the reference builtin
 
 
 @pytest.mark.gpu
@@ -126,10 +127,12 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 49 and evals >= 49 and fallbacks == 1, (stats, err)    # 28 values + 21 gradients; 1 untranslatable
+    assert translated == 56 and evals >= 56 and fallbacks == 1, (stats, err)    # 28 values + 21 gradients + 7 potentials; 1 untranslatable
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
-    compare(ref[cut:], new[cut:-1], 2e-9)        # finite differences: round-off of f amplified by 1/(2 eps)
+    cut2 = ref.index("-- potentials")
+    compare(ref[cut:cut2], new[cut:cut2], 2e-9)   # finite differences: round-off of f amplified by 1/(2 eps)
+    compare(ref[cut2:], new[cut2:-1], 1e-9)       # potentials: exact gradient function 1e-12-ish, FD variant 1e-10
 
 
 @pytest.mark.gpu

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.integral_cases import CASES, GRAD_CASES, fields_for, meshes
+from tests.golden.integral_cases import CASES, GRAD_CASES, POT_CASES, fields_for, meshes
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "integrals.npz")
 TOL = 1e-12
@@ -135,6 +135,23 @@ def test_device_integral_gradients_match_vm_goldens(mb, gcase):
     err = np.max(np.abs(got.ravel() - gold)) / np.max(np.abs(gold))
     print(gname, wrt, f"err {err:.2e}")
     assert err <= 2e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pcase", POT_CASES, ids=[c[0] for c in POT_CASES])
+def test_scalar_potential_matches_vm_goldens(mb, pcase):
+    name, mesh, fn, gradfn, _, _, sel = pcase
+    G = np.load(GOLD)
+    v, gr = meshes()[mesh]
+    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2))
+    args = [m] + ([mb.Selection(m, ids={0: sel})] if sel is not None else [])
+    pot = mb.ScalarPotential(fn, gradfn)
+    integrand, total, grad = pot.integrand(*args), pot.total(*args), pot.gradient(*args)
+    gi, gt, gg = G[name + "__integrand"], float(G[name + "__total"][0]), G[name + "__gradient"]
+    assert np.max(np.abs(integrand - gi)) <= TOL * np.max(np.abs(gi))
+    assert abs(total - gt) <= TOL * max(abs(gt), np.max(np.abs(gi)))
+    tol = TOL if gradfn is not None else 2e-9          # explicit gradient function: exact; otherwise central differences
+    assert np.max(np.abs(grad.ravel() - gg)) <= tol * np.max(np.abs(gg)), name
 
 
 @pytest.mark.gpu
