@@ -155,11 +155,18 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_grad_gather(McuParams p, McuView 
     if (myflags) atomicOr(flags, myflags);  // status word only; never data
 }
 
+// The finite-difference kernels evaluate heavy integrands (Nematic: ~700 instructions per evaluation) with long FP64
+// dependency chains; unconstrained they take ~150 registers = one 256-thread block per SM and stall on latency.
+// Two resident blocks (<= 128 registers) hide it better.
+#ifndef MCU_FD_MINBLOCKS
+#define MCU_FD_MINBLOCKS 2
+#endif
+
 // Central differences with respect to the coordinates of one vertex, summed over the
 // incident elements in ascending id: frc = f0 + (fp - fm)/(2 eps) per coordinate
 // (functional_numericalgrad, functional.c:1142-1162).
 template <int F, int SH>
-__global__ void __launch_bounds__(MCU_BLOCK) k_fd_grad(McuParams p, McuView v, double *out) {
+__global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_grad(McuParams p, McuView v, double *out) {
     int vtx = blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (vtx >= p.nv) return;
     const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps = Shape<SH>::ps(p);
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_grad(McuParams p, McuView v, d
 // Central differences with respect to the field degrees of freedom stored at one vertex
 // (functional_numericalfieldgrad, functional.c:1305-1328).
 template <int F, int SH>
-__global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView v, double *out) {
+__global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_fieldgrad(McuParams p, McuView v, double *out) {
     int vtx = blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (vtx >= p.nv) return;
     const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps0 = Shape<SH>::ps(p);
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_fieldgrad(McuParams p, McuView
 // — the order in which functional_numericalgrad / functional_numericalfieldgrad accumulate (functional.c:1142-1162,
 // 1305-1328), so the result is bit-identical to the vertex-centric kernels'.
 template <int F, int SH, bool FIELD>
-__global__ void __launch_bounds__(MCU_BLOCK) k_fd_elem(McuParams p, McuView v, double *scratch) {
+__global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_elem(McuParams p, McuView v, double *scratch) {
     const int nv = Shape<SH>::nv(p), dim = Shape<SH>::dim(p), ps0 = Shape<SH>::ps(p);
     const int nc = FIELD ? (p.wrt == 0 ? ps0 : p.psize1) : dim;
     const long t = (long) blockIdx.x * MCU_BLOCK + threadIdx.x;
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(MCU_BLOCK) k_fd_elem(McuParams p, McuView v, d
 // arithmetic of every number that IS recomputed is the one gradsq_integrand performs (same helper functions, same
 // order), so the differences are bit-identical to re-evaluating the whole integrand twice per degree of freedom.
 template <int NV, int PS>
-__global__ void __launch_bounds__(MCU_BLOCK) k_gradsq_fd_elem(McuParams p, McuView v, double *scratch) {
+__global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_gradsq_fd_elem(McuParams p, McuView v, double *scratch) {
     const long t = (long) blockIdx.x * MCU_BLOCK + threadIdx.x;
     if (t >= (long) v.n * NV) return;
     const int ce = (int) (t / NV), corner = (int) (t - (long) ce * NV);

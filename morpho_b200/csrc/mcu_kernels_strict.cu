@@ -155,13 +155,3 @@ cudaError_t mcu_strict_gradient(const McuParams &p, const McuView &v, double *d_
     DISPATCH(CALL)
 #undef CALL
 }
-
-cudaError_t mcu_strict_fieldgradient(const McuParams &p, const McuView &v, double *d_out, cudaStream_t st) {
-    switch (p.functional) {
-        case MCU_F_GRADSQ: return run_fd_fieldgrad<MCU_F_GRADSQ>(p, v, d_out, st);
-        case MCU_F_NORMSQ: return run_fd_fieldgrad<MCU_F_NORMSQ>(p, v, d_out, st);
-        case MCU_F_NEMATIC: return run_fd_fieldgrad<MCU_F_NEMATIC>(p, v, d_out, st);
-        case MCU_F_NEMATICELECTRIC: return run_fd_fieldgrad<MCU_F_NEMATICELECTRIC>(p, v, d_out, st);
-    }
-    return cudaErrorInvalidValue;
-}
