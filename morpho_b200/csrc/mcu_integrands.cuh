@@ -168,6 +168,23 @@ __device__ __forceinline__ void p1grad_tri_apply(int dim, const double (*t)[3], 
     for (int k = 0; k < 3; k++) if (k < dim) out[k] = ((0.0 + v0 * t[0][k]) + v1 * t[1][k]) + v2 * t[2][k];
 }
 
+// What the field functionals need from the vertex positions alone: element size and the factors of the P1 gradient.
+// The finite-difference field gradients perturb field values only, so they compute it once per element.
+struct ElemGeom { double size; TetLU lu; double t[3][3]; };
+__device__ __forceinline__ void elem_geom(int g, int dim, const double (*x)[3], ElemGeom &gm) {
+    gm.size = elem_size(g, x);
+    if (g == 2) p1grad_tri_factor(dim, x, gm.t);
+    else if (g == 3) p1grad_tet_factor(x, gm.lu);
+}
+// p1grad_tri / p1grad_tet with the factors taken from gm: the same operations on the values, in the same order
+__device__ __forceinline__ void p1grad_cached(int g, int dim, const ElemGeom &gm, int nvals, const double *vals, int stride, double *out) {
+#pragma unroll
+    for (int v = 0; v < nvals; v++) {
+        if (g == 2) p1grad_tri_apply(dim, gm.t, vals[v], vals[stride + v], vals[2 * stride + v], out + v * dim);
+        else p1grad_tet_solve(gm.lu, vals[v], vals[stride + v], vals[2 * stride + v], vals[3 * stride + v], out + v * 3);
+    }
+}
+
 // nematic_bcintf / nematic_bcintfg (functional.c:3818-3834): exact barycentric integrals
 __device__ __forceinline__ double bcintf(int n, const double *f) {
     double sum = 0;
@@ -187,26 +204,28 @@ __device__ __forceinline__ double bcintfg(int n, const double *f, const double *
 }
 
 // gradsq_integrand (functional.c:3657-3676): size * |grad q|_F^2
-__device__ __forceinline__ double gradsq_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+__device__ __forceinline__ double gradsq_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps, const ElemGeom *gm = nullptr) {
     const int g = nv - 1;
     double grad[MCU_MAXPSIZE * 3];
-    double size = elem_size(g, d.x);
-    if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
+    double size = gm ? gm->size : elem_size(g, d.x);
+    if (gm) p1grad_cached(g, dim, *gm, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
+    else if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
     else p1grad_tet(d.x, ps, &d.q[0][0], MCU_MAXPSIZE, grad);
     double gradnrm = vnorm(ps * dim, grad);
     return gradnrm * gradnrm * size;
 }
 
 // nematic_integrand (functional.c:3837-3923): Frank energy with a P1 director
-__device__ __forceinline__ double nematic_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+__device__ __forceinline__ double nematic_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps, const ElemGeom *gm = nullptr) {
     const int g = nv - 1;
     double gradnnraw[MCU_MAXPSIZE * 3], gradnn[9], curlnn[3];
 #pragma unroll
     for (int i = 0; i < 9; i++) gradnn[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < ps * 3; i++) gradnnraw[i] = 0.0;
-    double size = elem_size(g, d.x);
-    if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
+    double size = gm ? gm->size : elem_size(g, d.x);
+    if (gm) p1grad_cached(g, dim, *gm, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
+    else if (g == 2) p1grad_tri(dim, d.x, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
     else if (g == 3) p1grad_tet(d.x, ps, &d.q[0][0], MCU_MAXPSIZE, gradnnraw);
 #pragma unroll
     for (int j = 0; j < 3; j++)
@@ -243,11 +262,12 @@ __device__ __forceinline__ double nematic_integrand(const McuParams &p, const El
 }
 
 // nematicelectric_integrand (functional.c:4053-4092): size * E_i E_j <n_i n_j>, E = grad(phi)
-__device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+__device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps, const ElemGeom *gm = nullptr) {
     const int g = nv - 1;
     double ee[3] = {0.0, 0.0, 0.0};
-    double size = elem_size(g, d.x);
-    if (g == 2) p1grad_tri(dim, d.x, 1, d.phi, 1, ee);
+    double size = gm ? gm->size : elem_size(g, d.x);
+    if (gm) p1grad_cached(g, dim, *gm, 1, d.phi, 1, ee);
+    else if (g == 2) p1grad_tri(dim, d.x, 1, d.phi, 1, ee);
     else if (g == 3) p1grad_tet(d.x, 1, d.phi, 1, ee);
     double nnt[3][MCU_MAXNV];
 #pragma unroll
@@ -267,7 +287,7 @@ __device__ __forceinline__ double nematicelectric_integrand(const McuParams &p, 
 // (nv, dim, ps) = vertices per element, coordinates per vertex, doubles per field entry: literal constants in the
 // shape-specialised kernels (everything below unrolls and the element data stays in registers), p's values otherwise.
 template <int F>
-__device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps) {
+__device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemData &d, int nv, int dim, int ps, const ElemGeom *gm = nullptr) {
     if (F == MCU_F_LENGTH) return elem_size(1, d.x);
     if (F == MCU_F_AREAENCLOSED) {
 #ifdef MCU_STRICT
@@ -282,9 +302,9 @@ __device__ __forceinline__ double eval_integrand(const McuParams &p, const ElemD
     if (F == MCU_F_AREA) return elem_size(2, d.x);
     if (F == MCU_F_VOLUMEENCLOSED) return volumeenclosed_of(d.x);
     if (F == MCU_F_VOLUME) return volume_of(d.x);
-    if (F == MCU_F_GRADSQ) return gradsq_integrand(p, d, nv, dim, ps);
-    if (F == MCU_F_NEMATIC) return nematic_integrand(p, d, nv, dim, ps);
-    if (F == MCU_F_NEMATICELECTRIC) return nematicelectric_integrand(p, d, nv, dim, ps);
+    if (F == MCU_F_GRADSQ) return gradsq_integrand(p, d, nv, dim, ps, gm);
+    if (F == MCU_F_NEMATIC) return nematic_integrand(p, d, nv, dim, ps, gm);
+    if (F == MCU_F_NEMATICELECTRIC) return nematicelectric_integrand(p, d, nv, dim, ps, gm);
     if (F == MCU_F_NORMSQ) return dotn(ps, d.q[0], d.q[0]);  // normsq_integrand, functional.c:4149-4160
     return 0.0;
 }

@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_elem(McuPara
     ElemData d;
     gather_elem<F>(p, v, ids, d, nv, dim, ps0);
     double *o = scratch + (size_t) t * nc;
+    // field perturbations leave the geometry alone: element size and P1-gradient factors are computed once
+    ElemGeom gm;
+    const ElemGeom *gmp = nullptr;
+    if (FIELD && (F == MCU_F_GRADSQ || F == MCU_F_NEMATIC || F == MCU_F_NEMATICELECTRIC) && nv >= 3) { elem_geom(nv - 1, dim, d.x, gm); gmp = &gm; }
     if (!FIELD) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -326,9 +330,9 @@ __global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_elem(McuPara
             double f0 = (p.wrt == 0) ? elem_getq(d, corner, i) : elem_getphi(d, corner);
             double eps = fdstepsize(f0);
             if (p.wrt == 0) elem_setq(d, corner, i, f0 + eps); else elem_setphi(d, corner, f0 + eps);
-            double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+            double fr = eval_integrand<F>(p, d, nv, dim, ps0, gmp);
             if (p.wrt == 0) elem_setq(d, corner, i, f0 - eps); else elem_setphi(d, corner, f0 - eps);
-            double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+            double fl = eval_integrand<F>(p, d, nv, dim, ps0, gmp);
             if (p.wrt == 0) elem_setq(d, corner, i, f0); else elem_setphi(d, corner, f0);
             o[i] = (fr - fl) / (2 * eps);
         }
@@ -338,9 +342,9 @@ __global__ void __launch_bounds__(MCU_BLOCK, MCU_FD_MINBLOCKS) k_fd_elem(McuPara
             double f0 = *slot;
             double eps = fdstepsize(f0);
             *slot = f0 + eps;
-            double fr = eval_integrand<F>(p, d, nv, dim, ps0);
+            double fr = eval_integrand<F>(p, d, nv, dim, ps0, gmp);
             *slot = f0 - eps;
-            double fl = eval_integrand<F>(p, d, nv, dim, ps0);
+            double fl = eval_integrand<F>(p, d, nv, dim, ps0, gmp);
             *slot = f0;
             o[i] = (fr - fl) / (2 * eps);
         }
