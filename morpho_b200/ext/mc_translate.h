@@ -286,9 +286,9 @@ static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym
     if (func->nargs != nargs || func->varg >= 0 || func->opt.count > 0 || func->nopt > 0) return mt_fail(c, "argument count / optional arguments");
     if (++c->depth > MT_MAXDEPTH) return mt_fail(c, "call depth");
     if (!c->v->instructions) return mt_fail(c, "no program");
-    mt_sym *reg = (mt_sym *) malloc(sizeof(mt_sym) * (MORPHO_MAXREGISTERS + 1));
+    mt_sym *reg = (mt_sym *) malloc(sizeof(mt_sym) * (MORPHO_MAXREGISTERS + 8));      /* INVOKE touches reg[a + 2] */
     if (!reg) return mt_fail(c, "allocation");
-    for (int i = 0; i <= MORPHO_MAXREGISTERS; i++) reg[i] = mt_none();
+    for (int i = 0; i < MORPHO_MAXREGISTERS + 8; i++) reg[i] = mt_none();
     reg[0] = mt_none(); reg[0].kind = MT_OBJ; reg[0].obj = fn;
     for (int i = 0; i < nargs; i++) reg[i + 1] = args[i];
     for (int i = nargs + 1; i < func->nregs && i <= MORPHO_MAXREGISTERS; i++) reg[i] = mt_num(mt_consti(c, 0));   /* vm.c:733 */
