@@ -35,6 +35,8 @@ typedef struct {
     vm *v;
     mt_node nodes[MT_MAXNODES];
     int nnodes, depth, dim;
+    int nfields, fqbase[16], frows[16], fcols[16];      /* the Field arguments: first flattened component and shape */
+    value fieldobj[16];                                  /* the Field objects themselves, for grad(Field) (functional.c:4644-4646) */
     const char *why;
 } mt_ctx;
 
@@ -255,13 +257,24 @@ static bool mt_call(mt_ctx *c, const mt_sym *callee, const mt_sym *args, int nar
     }
     if (nargs == 1 && !strcmp(name, "grad")) {
         const mt_sym *q = &args[0];
-        if (q->field < 0) return mt_fail(c, "grad() of something that is not a Field argument");
+        int fk = q->field;
+        if (fk < 0 && q->kind == MT_OBJ)            /* the Field object itself instead of its interpolated value */
+            for (int k = 0; k < c->nfields; k++) if (MORPHO_ISOBJECT(c->fieldobj[k]) && MORPHO_GETOBJECT(c->fieldobj[k]) == MORPHO_GETOBJECT(q->obj)) { fk = k; break; }
+        if (fk < 0 || fk >= c->nfields) return mt_fail(c, "grad() of something that is not a Field argument");
+        if (q->kind == MT_NUM) {
+            /* The reference finds the Field of an interpolated NUMBER by comparing values (functional.c:4647-4651) and
+             * raises IntgrlAmbgsFld when two scalar quantities coincide at a node: data dependent, so with more than
+             * one scalar Field the closure stays on the reference builtin. */
+            int nscalar = 0;
+            for (int k = 0; k < c->nfields; k++) if (c->frows[k] == 0) nscalar++;
+            if (nscalar > 1) return mt_fail(c, "grad() of an interpolated scalar with several scalar Fields (resolved by value in the reference)");
+        }
         *out = mt_none();
-        if (q->kind == MT_NUM) {                    /* scalar Field: a dim x 1 Matrix (integral_gradalloc) */
+        if (c->frows[fk] == 0) {                    /* scalar Field: a dim x 1 Matrix (integral_gradalloc) */
             out->kind = MT_VEC; out->nrows = c->dim; out->ncols = 1;
-            for (int k = 0; k < c->dim; k++) out->node[k] = mt_new(c, MCU_X_GRADQ, 3 * q->qbase + k, 0, 0.0, 0);
+            for (int k = 0; k < c->dim; k++) out->node[k] = mt_new(c, MCU_X_GRADQ, 3 * c->fqbase[fk] + k, 0, 0.0, 0);
         } else {                                    /* Matrix prototype: a List of dim matrices, [k] = d q / d x_k */
-            out->kind = MT_GRADLIST; out->nrows = q->nrows; out->ncols = q->ncols; out->qbase = q->qbase;
+            out->kind = MT_GRADLIST; out->nrows = c->frows[fk]; out->ncols = c->fcols[fk]; out->qbase = c->fqbase[fk];
         }
         return true;
     }
@@ -407,7 +420,7 @@ static bool mt_emit(mt_ctx *c, int node, mcu_expr_op *prog, int *n, int cap) {
 
 /* Entry point.  fieldrows/fieldcols: shape of every Field's Matrix prototype (rows 0 = scalar Field), in argument order. */
 static bool mc_translate_integrand(vm *v, value fn, int dim, int nfields, const int *fieldrows, const int *fieldcols,
-                                   mcu_expr_op *prog, int cap, int *nops, const char **why) {
+                                   const value *fieldvals, mcu_expr_op *prog, int cap, int *nops, const char **why) {
     mt_ctx *c = (mt_ctx *) calloc(1, sizeof(mt_ctx));
     if (!c) { *why = "allocation"; return false; }
     c->v = v;
@@ -418,9 +431,12 @@ static bool mc_translate_integrand(vm *v, value fn, int dim, int nfields, const 
         args[0] = mt_none(); args[0].kind = MT_VEC; args[0].nrows = dim; args[0].ncols = 1;
         for (int i = 0; i < dim; i++) args[0].node[i] = mt_new(c, MCU_X_POS, i, 0, 0.0, 0);
         int q = 0;
+        c->nfields = nfields;
         for (int k = 0; k < nfields && ok; k++) {
             mt_sym *s = &args[k + 1];
             *s = mt_none();
+            c->fqbase[k] = q; c->frows[k] = fieldrows[k]; c->fcols[k] = fieldcols[k];
+            c->fieldobj[k] = fieldvals ? fieldvals[k] : MORPHO_NIL;
             if (fieldrows[k] == 0) {                 /* scalar Field: the quantity is a Float */
                 *s = mt_num(mt_new(c, MCU_X_FIELD, q, 0, 0.0, 0));
                 s->field = k; s->qbase = q;

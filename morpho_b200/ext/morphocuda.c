@@ -443,7 +443,9 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     mcu_expr_op prog[MC_MAXPROG];
     int nops = 0;
     const char *why = "";
-    if (!mc_translate_integrand(v, fn, mr->dim, nf, rows, cols, prog, MC_MAXPROG, &nops, &why)) {
+    value fvals[16];
+    for (int i = 0; i < nf; i++) fvals[i] = MORPHO_OBJECT(flds[i]);
+    if (!mc_translate_integrand(v, fn, mr->dim, nf, rows, cols, fvals, prog, MC_MAXPROG, &nops, &why)) {
         mc_log("integrand not translated:", why);
         return false;
     }
@@ -710,7 +712,7 @@ static value mc_translate_fn(vm *v, int nargs, value *args) {
     mcu_expr_op prog[MC_MAXPROG];
     int nops = 0;
     const char *why = "";
-    if (!mc_translate_integrand(v, MORPHO_GETARG(args, 0), MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 1)), nf, rows, cols, prog, MC_MAXPROG, &nops, &why)) {
+    if (!mc_translate_integrand(v, MORPHO_GETARG(args, 0), MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 1)), nf, rows, cols, NULL, prog, MC_MAXPROG, &nops, &why)) {
         value s = object_stringfromcstring(why, strlen(why));
         return morpho_wrapandbind(v, MORPHO_GETOBJECT(s));
     }

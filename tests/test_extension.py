@@ -127,7 +127,7 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 56 and evals >= 56 and fallbacks == 1, (stats, err)    # 28 values + 21 gradients + 7 potentials; 1 untranslatable
+    assert translated == 59 and evals >= 59 and fallbacks == 1, (stats, err)    # 30 values + 22 gradients + 7 potentials; 1 untranslatable
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
     cut2 = ref.index("-- potentials")
