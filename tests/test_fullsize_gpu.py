@@ -116,6 +116,22 @@ def test_config4_tactoid_disk_4m(mb, oracle):
     assert abs(A - oracle.total(v, conn, FunctionalSpec("Area"))) <= TOL_EXACT * A
     ns = mb.NormSq(fld)
     assert abs(ns.total(m) - m.nv) <= 1e-10 * m.nv            # unit director: sum |n|^2 = number of vertices
+    # the closure integrals of config 4 at full size (anchoring on the boundary, bulk terms on the sheet), through
+    # properties that do not need the CPU: |t| = 1 and |n| = 1 make the integrals the length / the area; the P1
+    # gradient of a linear field is exact; and the integrand map sums to the total
+    from morpho_b200.integrand import grad, normal, tangent
+    li = mb.LineIntegral(lambda x: tangent()[0] ** 2 + tangent()[1] ** 2 + tangent()[2] ** 2)
+    assert abs(li.total(m) - L.total(m)) <= 1e-12 * L.total(m)
+    anch = mb.LineIntegral(lambda x, q: (q[0] * tangent()[0] + q[1] * tangent()[1] + q[2] * tangent()[2]) ** 2, fld)
+    ai = anch.integrand(m)
+    assert ai.shape == (bnd.shape[0],) and np.all(ai >= 0) and np.all(ai <= L.integrand(m) * (1 + 1e-12))
+    assert abs(ai.sum() - anch.total(m)) <= 1e-12 * anch.total(m)
+    one = mb.AreaIntegral(lambda x: normal()[0] ** 2 + normal()[1] ** 2 + normal()[2] ** 2)
+    assert abs(one.total(m) - A) <= 1e-12 * A
+    lin = mb.Field(m, (2.0 * v[:, 0] - 3.0 * v[:, 1] + 0.5).reshape(-1, 1))
+    gsq = mb.AreaIntegral(lambda x, p: grad(p)[0] ** 2 + grad(p)[1] ** 2 + grad(p)[2] ** 2, lin)
+    assert abs(gsq.total(m) - 13.0 * A) <= 1e-9 * A                     # flat sheet: |grad|^2 = 4 + 9
+    assert abs(gsq.total(m) - mb.GradSq(lin).total(m)) <= 1e-11 * A     # the same number through the GradSq functional
 
 
 def test_config5_tet_cube_50m(mb, oracle):
