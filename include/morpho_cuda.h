@@ -190,6 +190,10 @@ int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *p
                  int mode, double *host_out);
 int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff,
                         int mode, double *dev_out);
+/* Row block [row0, row0 + nrows) of the interaction against all n points: the per-GPU share of the row-block partition
+ * (SURVEY 8e); outputs are indexed by row - row0; MCU_TOTAL gives the partial energy of the block. */
+int mcu_pairwise_rows_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff,
+                             int mode, int row0, int nrows, double *dev_out);
 
 /* ---- element partition across GPUs: functional_binbounds (functional.c:863-879) ---- */
 int mcu_binbounds(int nel, int nbins, int *bounds);

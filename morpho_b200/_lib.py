@@ -89,6 +89,7 @@ def lib():
         "mcu_result_size": (C.c_long, [vp, C.POINTER(McuFunctional), C.c_int]),
         "mcu_pairwise": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
+        "mcu_pairwise_rows_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, C.c_int, C.c_int, vp]),
         "mcu_binbounds": (C.c_int, [C.c_int, C.c_int, vp]),
         "mcu_timer_start": (C.c_int, []),
         "mcu_timer_stop": (C.c_int, [C.POINTER(C.c_float)]),

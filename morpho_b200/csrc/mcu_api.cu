@@ -620,6 +620,21 @@ int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const dou
     return MCU_OK;
 }
 
+/* rows [row0, row0 + nrows) of the all-pairs interaction: the block one GPU computes when the N x N matrix is
+ * partitioned by rows across GPUs (every GPU holds all n positions).  dev_out: nrows (MCU_INTEGRAND), nrows * dim
+ * (MCU_GRADIENT) doubles, or the partial energy of those rows (MCU_TOTAL, 1 double). */
+int mcu_pairwise_rows_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff, int mode,
+                             int row0, int nrows, double *dev_out) {
+    NEED_INIT();
+    (void) params;
+    if (n < 0 || (dim != 2 && dim != 3) || !dev_x || !dev_out || kind != 0 || row0 < 0 || nrows < 0 || row0 + nrows > n) { mcu_set_error("bad pairwise arguments"); return MCU_ERR_ARGS; }
+    static CompSum *partials = nullptr;
+    if (!partials) CK(cudaMalloc((void **) &partials, sizeof(CompSum) * 4096));
+    cudaError_t e = mcu_pairwise_launch(n, dim, dev_x, kind, cutoff, mode, dev_out, partials, g_stream, row0, nrows);
+    if (e != cudaSuccess) { mcu_set_error("pairwise launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
+    return MCU_OK;
+}
+
 int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *params, double cutoff, int mode, double *host_out) {
     NEED_INIT();
     if (n < 0 || !host_x || !host_out) return MCU_ERR_ARGS;

@@ -26,4 +26,4 @@ int mcu_patchset_attach_push(McuPatchSet *ps, int nv, int n, const int *vertex, 
 
 // All-pairs kernels.
 cudaError_t mcu_pairwise_launch(int n, int dim, const double *d_x, int kind, double cutoff, int mode,
-                                double *d_out, CompSum *partials, cudaStream_t st);
+                                double *d_out, CompSum *partials, cudaStream_t st, int row0 = 0, int nrows = -1);

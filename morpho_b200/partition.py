@@ -285,3 +285,33 @@ def reduce_total(local_total: float, torch, dist) -> float:
     for p in parts:
         total += float(p.item())
     return total
+
+
+def pairwise_partitioned(x: np.ndarray, mode: int, torch, dist, kind: int = 0, cutoff=None):
+    """PairwisePotential on several GPUs: the N x N interaction matrix is cut into row blocks with the
+    reference's own bin bounds (functional_binbounds), every rank holds all N positions and computes the rows of its
+    block against all points (``mcu_pairwise_rows_device``).  No exchange on the data path: the blocks are
+    concatenated with one all-gather at the end (integrand / gradient), the energy is the fixed-order sum of the
+    per-rank partial energies (:func:`reduce_total`).  Returns the full result on every rank."""
+    import ctypes as C
+    from . import _lib
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n, dim = x.shape
+    b = binbounds(n, world)
+    r0, nr = int(b[rank]), int(b[rank + 1] - b[rank])
+    L = _lib.lib()
+    dx = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+    ncol = {_lib.MCU_TOTAL: 0, _lib.MCU_INTEGRAND: 1, _lib.MCU_GRADIENT: dim}[mode]
+    maxr = int(np.max(np.diff(b)))
+    out = torch.zeros(max(maxr * max(ncol, 1), 1), dtype=torch.float64, device="cuda")
+    _lib.check(L.mcu_pairwise_rows_device(n, dim, dx.data_ptr(), kind, None, C.c_double(float(cutoff) if cutoff else 0.0), mode, r0, nr, out.data_ptr()))
+    L.mcu_sync()
+    if mode == _lib.MCU_TOTAL:
+        return reduce_total(float(out[0].item()), torch, dist)
+    if world == 1:
+        return out[: nr * ncol].cpu().numpy().reshape(n, ncol) if ncol > 1 else out[:nr].cpu().numpy()
+    parts = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(parts, out)                       # equal-size padded blocks
+    full = np.concatenate([parts[r][: int(b[r + 1] - b[r]) * ncol].cpu().numpy() for r in range(world)])
+    return full.reshape(n, ncol) if ncol > 1 else full

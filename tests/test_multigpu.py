@@ -168,3 +168,52 @@ def test_partitioned_tet_mesh_over_peer_memory():
     for rank, errs in res:
         assert errs[0] <= 1e-12 and errs[1] <= 1e-12, (rank, errs)     # analytic gradient and total
         assert errs[2] <= 2e-9, (rank, errs)                             # finite-difference field gradient
+
+
+def _worker_pairwise(rank, world, port, n, q):
+    """Config 3 in miniature on two GPUs: row blocks of the all-pairs interaction, no exchange until the final
+    concatenation; against the oracle's i<j double loop on the whole point set."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import morpho_b200 as mb
+        from morpho_b200 import _lib, meshgen as mg
+        from morpho_b200.partition import pairwise_partitioned
+        from oracle.oracle import Oracle
+        mb.init(rank)
+        x = mg.sphere_points(n, seed=77)
+        O = Oracle()
+        e_ref, g_ref = O.pairwise_coulomb(x, "integrand"), O.pairwise_coulomb(x, "gradient")
+        e = pairwise_partitioned(x, _lib.MCU_INTEGRAND, torch, dist)
+        g = pairwise_partitioned(x, _lib.MCU_GRADIENT, torch, dist)
+        tot = pairwise_partitioned(x, _lib.MCU_TOTAL, torch, dist)
+        errs = [np.max(np.abs(e - e_ref)) / np.max(np.abs(e_ref)),
+                np.max(np.linalg.norm(g - g_ref, axis=1)) / np.max(np.linalg.norm(g_ref, axis=1)),
+                abs(tot - e_ref.sum()) / abs(e_ref.sum())]
+        q.put((rank, errs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partitioned_pairwise_row_blocks():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pairwise, args=(r, world, port, 3001, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        assert max(errs) <= 1e-12, (rank, errs)
