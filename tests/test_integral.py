@@ -189,3 +189,36 @@ def test_integral_rejects_bad_programs(mb):
     f._prog[1][0] = (3, 0, 0.0)                           # ADD on an empty stack
     with pytest.raises(mb.MorphoError):
         f.total(m)
+
+
+@pytest.mark.gpu
+def test_integral_edge_cases(mb, reference):
+    """Empty selections, zero-size elements, a 2-D mesh, an integrand that is singular on part of the mesh: the device
+    does what the reference's integrator does (same values, zeros where the reference leaves zeros)."""
+    from morpho_b200.integrand import exp, sqrt
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [1, 0, 0], [2, 2, 0.5]], dtype=np.float64)
+    faces = np.array([[0, 1, 2], [0, 2, 3], [1, 2, 4], [2, 3, 5]], dtype=np.int32)          # face 2 has zero area (1 and 4 coincide)
+    faces.sort(axis=1)
+    edges = np.array([[0, 1], [1, 2], [1, 4], [3, 5]], dtype=np.int32)                      # edge 2 has zero length
+    m = mb.Mesh(v, edges=edges, faces=faces)
+    rm = reference.mesh(v, {1: edges, 2: faces})
+    fn = lambda x: exp(x[0]) * sqrt(1.0 + x[1] * x[1]) + x[2]                                # noqa: E731
+    for grade, cls in ((1, mb.LineIntegral), (2, mb.AreaIntegral)):
+        prog = _prog(fn, 3, [], {})
+        want = rm.integral(grade, [tuple(t) for t in prog.tolist()])
+        got = cls(fn).integrand(m)
+        assert np.max(np.abs(got - want)) <= TOL * np.max(np.abs(want))
+        assert got[2] == 0.0                                                                 # the degenerate element contributes nothing
+        empty = mb.Selection(m, ids={grade: np.zeros(0, dtype=np.int32)})
+        assert cls(fn).total(m, empty) == 0.0 and not np.any(cls(fn).integrand(m, empty))
+        assert not np.any(cls(fn).gradient(m, empty))
+    rm.free()
+    # 2-D mesh: positions have two coordinates, x[2] is out of range for the program validator
+    v2 = np.ascontiguousarray(v[:4, :2])
+    m2 = mb.Mesh(v2, faces=faces[:2])
+    assert abs(mb.AreaIntegral(lambda x: x[0] * x[1]).total(m2) - 0.25) <= 1e-14
+    with pytest.raises((IndexError, mb.MorphoError)):                # the reference raises an index error too
+        mb.AreaIntegral(lambda x: x[2]).total(m2)
+    # an integrand with a (integrable) singularity at a vertex: the adaptive rule refines to its depth limit and returns
+    r = mb.AreaIntegral(lambda x: 1.0 / sqrt(x[0] * x[0] + x[1] * x[1] + 1e-300)).integrand(m2)
+    assert np.all(np.isfinite(r)) and abs(r.sum() - 2.0 * np.log(1.0 + np.sqrt(2.0))) < 1e-3     # int_0^1 int_0^1 1/r = 2 asinh(1)
