@@ -242,6 +242,8 @@ int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, in
 
 /* timeline diagnostics of the patch kernel (measurement aid): dev_buf receives, per consumer warp of every CTA,
  * {cycles waiting for data, cycles alive}; NULL disarms. */
+int mcu_debug_patch_triangles(int nv, int nel, const int *rix, const double *vert, int max_owned,
+                              long *n_words_out, int *tri_hdr_out, unsigned *tri_out);
 int mcu_debug_patch_profile(long long *dev_buf);
 
 #ifdef __cplusplus

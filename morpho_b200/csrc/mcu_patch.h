@@ -38,9 +38,16 @@ struct McuPatchRun {      // 8 bytes
 #ifndef MCU_PATCH_DESC_RUNS
 #define MCU_PATCH_DESC_RUNS 64        // = 32 lanes x producer warps
 #endif
-struct McuPatchDesc {     // 544 bytes
+struct McuPatchTri {      // 16 bytes: the triangle list of a patch (totals), see McuPatchPlan::tri
+    int off;              // offset of the staged list in McuPatchPlan::tri, in 16-byte units
+    int bytes;            // multiple of 16
+    int n_tri;
+    int pad;
+};
+struct McuPatchDesc {     // 560 bytes
     McuPatchHeader h;
     McuPatchRun runs[MCU_PATCH_DESC_RUNS];   // the first runs of the patch; the rest (rare) at runs[h.run_off + 64 ..]
+    McuPatchTri t;
 };
 
 // Staged table of a patch (32-bit words):
@@ -61,6 +68,12 @@ struct McuPatchPlan {
     std::vector<McuPatchHeader> hdr;
     std::vector<McuPatchRun> runs;
     std::vector<uint32_t> tab;       // all staged tables, each 16-byte aligned
+    // Triangle lists for the TOTALS: every triangle belongs to the patch that owns its smallest vertex id (all three
+    // vertices are local to that patch), so a total visits each triangle exactly once, one thread per triangle.
+    // Staged list (32-bit words): [0] index of the patch [1] n_tri [2],[3] 0, then n_tri entries of 4 x 16 bit
+    // (slot of vertex 0, 1, 2 in ascending global id, 0), padded to 16 bytes.
+    std::vector<McuPatchTri> tri_hdr;
+    std::vector<uint32_t> tri;
     int max_slots = 0, max_tab_bytes = 0, max_owned = 0, max_runs = 0;
     long n_halo = 0;                 // halo vertices over all patches (excluding alignment padding)
     long n_pad = 0;                  // slots that only exist for alignment
@@ -91,6 +104,7 @@ struct McuPatchSet {
     McuPatchDesc *d_desc = nullptr;
     McuPatchRun *d_runs = nullptr;
     uint32_t *d_tab = nullptr;
+    uint32_t *d_tri = nullptr;
     int *d_sched = nullptr;          // [0] next patch to hand out, [1] CTAs that ran out of work (self re-arming)
     int coords_bytes = 0, stage_bytes = 0, stages = 0, ctas_per_sm = 0;
 };

@@ -162,3 +162,33 @@ def test_patch_plan_handles_isolated_vertices(L):
         slot_gid, gids, offs, ents, _ = _decode_patch(P, h)
         owned.extend(int(g) for g in gids if g >= 0)
     assert sorted(owned) == list(range(v.shape[0]))
+
+
+@pytest.mark.parametrize("f,max_owned", [(3, 512), (12, 512), (30, 200)])
+def test_patch_triangle_lists_cover_every_triangle_once(L, f, max_owned):
+    """The totals walk per-patch triangle lists: every triangle of the mesh appears in exactly one list (the patch
+    that owns its smallest vertex), with the slots of its three vertices in ascending global id."""
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(f)
+    v = mg.perturb_radially(v)
+    P = _plan(L, v, c, max_owned)
+    nw = (C.c_long * 1)()
+    assert L.mcu_debug_patch_triangles(v.shape[0], c.shape[0], c.ctypes.data, v.ctypes.data, max_owned, nw, None, None) == 0
+    th = np.zeros((len(P["hdr"]), 4), dtype=np.int32)
+    tri = np.zeros(int(nw[0]), dtype=np.uint32)
+    assert L.mcu_debug_patch_triangles(v.shape[0], c.shape[0], c.ctypes.data, v.ctypes.data, max_owned, nw, th.ctypes.data, tri.ctypes.data) == 0
+    seen = {}
+    key = {tuple(t): i for i, t in enumerate(c.tolist())}
+    for pi, h in enumerate(P["hdr"]):
+        slot_gid, gids, offs, ents, patch_index = _decode_patch(P, h)
+        off, nbytes, n_tri, _ = (int(x) for x in th[pi])
+        words = tri[4 * off: 4 * off + nbytes // 4]
+        assert int(words[0]) == pi and int(words[1]) == n_tri and nbytes % 16 == 0 and nbytes >= 16 + 8 * n_tri
+        e = words[4: 4 + 2 * n_tri].view(np.uint16).reshape(n_tri, 4)
+        owned = set(int(g) for g in gids if g >= 0)
+        for s0, s1, s2, z in e.tolist():
+            t = (int(slot_gid[s0]), int(slot_gid[s1]), int(slot_gid[s2]))
+            assert z == 0 and t[0] < t[1] < t[2] and t[0] in owned
+            assert t in key and key[t] not in seen
+            seen[key[t]] = pi
+    assert len(seen) == c.shape[0]
