@@ -9,6 +9,9 @@ import morpho_b200 as mb
 from morpho_b200 import _lib, meshgen as mg
 f = int(sys.argv[1]) if len(sys.argv) > 1 else 707
 mb.init(0); L = mb.lib()
+for kv in sys.argv[2:]:                       # planner / kernel options, e.g. patch_stages=4
+    k, val = kv.split("=")
+    mb.set_option(k, int(val))
 v, c = mg.icosphere(f); v = mg.perturb_radially(v)
 m = mb.Mesh(v, faces=c)
 nel = c.shape[0]
