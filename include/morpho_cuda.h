@@ -117,6 +117,10 @@ int mcu_mesh_counts(const mcu_mesh *m, int *dim, int *nv, int nel[4]);
  * the reference's order of first discovery; built on the device (sort + scan).  mcu_mesh_get_connectivity copies the
  * incidence (nel * (g+1) ints) of any grade back. */
 int mcu_mesh_addgrade(mcu_mesh *m, int grade, int *nel_out);
+/* Selection(mesh, boundary=true) (selection_selectboundary, selection.c:211-232): ids, ascending, of the elements of
+ * grade maxgrade-1 contained in exactly one element of the top grade (for a line mesh: vertices with one incident line).
+ * *grade_out = that grade, *n_out = their number; at most cap ids are copied to host_ids (may be NULL to count). */
+int mcu_mesh_boundary(mcu_mesh *m, int *grade_out, int *n_out, int *host_ids, int cap);
 int mcu_mesh_get_connectivity(mcu_mesh *m, int grade, int *host_rix);
 /* vertex→element incidence as the reference builds it with sparse_transpose → cs_transpose
  * (sparse.c:1227-1244, mesh.c:663-685): tptr[nv+1], tidx[nel*(g+1)] element ids ascending per vertex. */

@@ -144,6 +144,113 @@ done:
     return rc;
 }
 
+// ---------------------------------------------------------------------------------
+// Boundary selection (selection_selectboundary, selection.c:211-232): the elements of grade max-1 contained in exactly
+// one element of the top grade.  The reference builds the raise matrix conn(max, max-1) with hash lookups; here the
+// facets of the top elements are generated as sort keys (the same candidates as addgrade), sorted by their leading
+// pair of ids, and every existing element of grade max-1 counts its occurrences with a binary search (+ a scan of
+// the short run of equal leading pairs for the third id of a triangular face).
+// ---------------------------------------------------------------------------------
+__global__ void k_count_containing(int nsub, int tuple, const int *__restrict__ sub_rix, long ncand,
+                                   const unsigned long long *__restrict__ key_sorted, const unsigned *__restrict__ val_sorted,
+                                   const unsigned *__restrict__ key_c, unsigned *__restrict__ flag) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nsub) return;
+    const int *ids = sub_rix + (size_t) e * tuple;
+    const unsigned long long key = ((unsigned long long) (unsigned) ids[0] << 32) | (unsigned) ids[1];
+    long lo = 0, hi = ncand;
+    while (lo < hi) { long mid = (lo + hi) >> 1; if (key_sorted[mid] < key) lo = mid + 1; else hi = mid; }
+    int count = 0;
+    for (long i = lo; i < ncand && key_sorted[i] == key; i++)
+        if (tuple == 2 || key_c[val_sorted[i]] == (unsigned) ids[2]) count++;
+    flag[e] = (count == 1) ? 1u : 0u;
+}
+
+__global__ void k_vertex_degree_one(int nv, const int *__restrict__ tptr, unsigned *__restrict__ flag) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) flag[v] = (tptr[v + 1] - tptr[v] == 1) ? 1u : 0u;
+}
+
+__global__ void k_compact(int n, const unsigned *__restrict__ flag, const unsigned *__restrict__ pos, int *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = i;
+}
+
+/* ids (ascending) of the boundary elements of grade maxgrade-1; *grade_out = that grade.  cap = room in host_ids;
+ * returns MCU_OK and the count in *n_out (ids beyond cap are dropped, the count is still the full one). */
+extern "C" int mcu_mesh_boundary(mcu_mesh *m, int *grade_out, int *n_out, int *host_ids, int cap) {
+    if (!m || !n_out) { mcu_set_error("boundary: null argument"); return MCU_ERR_ARGS; }
+    int top = 0;
+    for (int g = m->dim; g > 0 && !top; g--) if (m->conn[g].present) top = g;
+    if (top < 1) { mcu_set_error("boundary: the mesh has no elements"); return MCU_ERR_ELNOTFOUND; }       // SELECTION_BND
+    const int bnd = top - 1;
+    if (grade_out) *grade_out = bnd;
+    cudaStream_t st = mcu_stream();
+    int rc = MCU_OK, n_items = 0, nsel = 0;
+    unsigned *flag = nullptr, *pos = nullptr, *val[2] = {nullptr, nullptr}, *key_c = nullptr;
+    unsigned long long *key[2] = {nullptr, nullptr};
+    void *tmp = nullptr;
+    int *d_ids = nullptr;
+    size_t t1 = 0, t2 = 0;
+    unsigned last_flag = 0, last_pos = 0;
+    if (bnd == 0) {
+        rc = mcu_ensure_transpose(m, 1);
+        if (rc) return rc;
+        n_items = m->nv;
+        CKC(cudaMalloc((void **) &flag, 4 * (size_t) std::max(n_items, 1))); CKC(cudaMalloc((void **) &pos, 4 * (size_t) std::max(n_items, 1)));
+        if (n_items > 0) k_vertex_degree_one<<<(n_items + 255) / 256, 256, 0, st>>>(n_items, m->conn[1].d_tptr, flag);
+    } else {
+        if (!m->conn[bnd].present) { mcu_set_error("boundary: the mesh has no elements of grade %d (addgrade first)", bnd); return MCU_ERR_ELNOTFOUND; }
+        const McuConn &src = m->conn[top], &sub = m->conn[bnd];
+        Combos cb;
+        cb.n = bnd + 1; cb.nvper = top + 1; cb.ncomb = 0;
+        if (cb.n == 2) { for (int a = 0; a <= top; a++) for (int b = a + 1; b <= top; b++) { cb.idx[cb.ncomb][0] = a; cb.idx[cb.ncomb][1] = b; cb.idx[cb.ncomb][2] = 0; cb.ncomb++; } }
+        else { for (int a = 0; a <= top; a++) for (int b = a + 1; b <= top; b++) for (int c = b + 1; c <= top; c++) { cb.idx[cb.ncomb][0] = a; cb.idx[cb.ncomb][1] = b; cb.idx[cb.ncomb][2] = c; cb.ncomb++; } }
+        const long ncand = (long) src.nel * cb.ncomb;
+        if (ncand >= 4294967295L) { mcu_set_error("boundary: too many candidates"); return MCU_ERR_UNSUPPORTED; }
+        n_items = sub.nel;
+        const size_t nc = (size_t) std::max<long>(ncand, 1);
+        CKC(cudaMalloc((void **) &key[0], 8 * nc)); CKC(cudaMalloc((void **) &key[1], 8 * nc));
+        CKC(cudaMalloc((void **) &val[0], 4 * nc)); CKC(cudaMalloc((void **) &val[1], 4 * nc));
+        CKC(cudaMalloc((void **) &key_c, 4 * nc));
+        CKC(cudaMalloc((void **) &flag, 4 * (size_t) std::max(n_items, 1))); CKC(cudaMalloc((void **) &pos, 4 * (size_t) std::max(n_items, 1)));
+        if (ncand > 0) {
+            CKC(cub::DeviceRadixSort::SortPairs(nullptr, t1, key[0], key[1], val[0], val[1], (int) ncand, 0, 64, st));
+            CKC(cudaMalloc(&tmp, std::max<size_t>(t1, 16)));
+            k_candidates<<<(int) ((ncand + 255) / 256), 256, 0, st>>>(cb, src.nel, src.d_rix, key[0], key_c, val[0]);
+            CKC(cub::DeviceRadixSort::SortPairs(tmp, t1, key[0], key[1], val[0], val[1], (int) ncand, 0, 64, st));
+            cudaFree(tmp); tmp = nullptr;
+        }
+        if (n_items > 0) k_count_containing<<<(n_items + 255) / 256, 256, 0, st>>>(n_items, cb.n, sub.d_rix, ncand, key[1], val[1], key_c, flag);
+        g_mcu_launches += 2;
+    }
+    if (n_items > 0) {
+        CKC(cub::DeviceScan::ExclusiveSum(nullptr, t2, flag, pos, n_items, st));
+        CKC(cudaMalloc(&tmp, std::max<size_t>(t2, 16)));
+        CKC(cub::DeviceScan::ExclusiveSum(tmp, t2, flag, pos, n_items, st));
+        CKC(cudaMemcpyAsync(&last_flag, flag + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
+        CKC(cudaMemcpyAsync(&last_pos, pos + (n_items - 1), 4, cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+        nsel = (int) (last_flag + last_pos);
+        if (nsel > 0 && host_ids && cap > 0) {
+            CKC(cudaMalloc((void **) &d_ids, sizeof(int) * (size_t) nsel));
+            k_compact<<<(n_items + 255) / 256, 256, 0, st>>>(n_items, flag, pos, d_ids);
+            CKC(cudaMemcpyAsync(host_ids, d_ids, sizeof(int) * (size_t) std::min(nsel, cap), cudaMemcpyDeviceToHost, st));
+            CKC(cudaStreamSynchronize(st));
+            g_mcu_launches += 1;
+        }
+    }
+    *n_out = nsel;
+done:
+    for (int i = 0; i < 2; i++) { if (key[i]) cudaFree(key[i]); if (val[i]) cudaFree(val[i]); }
+    if (key_c) cudaFree(key_c);
+    if (flag) cudaFree(flag);
+    if (pos) cudaFree(pos);
+    if (tmp) cudaFree(tmp);
+    if (d_ids) cudaFree(d_ids);
+    return rc;
+}
+
 /* host copy of the incidence of grade g (nel * (g+1) ints, element ids in the reference's order) */
 extern "C" int mcu_mesh_get_connectivity(mcu_mesh *m, int g, int *host_rix) {
     if (!m || g < 1 || g > 3 || !m->conn[g].present || !host_rix) { mcu_set_error("get_connectivity: grade not present"); return MCU_ERR_ARGS; }

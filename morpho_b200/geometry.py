@@ -213,33 +213,22 @@ class Selection:
             self._select_boundary()
 
     def _select_boundary(self):
+        """selection_selectboundary (selection.c:211-232) on the device (mcu_mesh_boundary): elements of grade
+        maxgrade-1 contained in exactly one top element, plus their vertices (selection_addgradelower)."""
         m = self.mesh
         mg = m.maxgrade()
         if mg < 1:
             return
         bnd = mg - 1
-        if bnd == 0:
-            # boundary of a line mesh: vertices that belong to exactly one line
-            cnt = np.bincount(m._conn[1].ravel(), minlength=m.nv)
-            self._ids[0] = np.nonzero(cnt == 1)[0].astype(np.int32)
-            return
-        sub = m.addgrade(bnd)
-        top = m._conn[mg]
-        # a facet is on the boundary when exactly one top element contains it
-        from itertools import combinations
-        base = np.int64(m.nv)
-
-        def keys(a):
-            k = np.zeros(a.shape[0], dtype=np.int64)
-            for c in range(a.shape[1]):
-                k = k * base + a[:, c].astype(np.int64)
-            return k
-        cand = np.concatenate([top[:, list(c)] for c in combinations(range(mg + 1), bnd + 1)])
-        uk, cnt = np.unique(keys(cand), return_counts=True)
-        bkeys = uk[cnt == 1]
-        sel = np.nonzero(np.isin(keys(sub), bkeys))[0].astype(np.int32)
+        sub = m.addgrade(bnd) if bnd > 0 else None
+        cap = m.nv if bnd == 0 else sub.shape[0]
+        ids = np.zeros(max(cap, 1), dtype=np.int32)
+        g, n = C.c_int(), C.c_int()
+        check(lib().mcu_mesh_boundary(m._h, C.byref(g), C.byref(n), ids.ctypes.data, cap))
+        sel = ids[: n.value].copy()
         self._ids[bnd] = sel
-        self._ids[0] = np.unique(sub[sel].ravel()).astype(np.int32)   # selection_addgradelower(sel, 0)
+        if bnd > 0:
+            self._ids[0] = np.unique(sub[sel].ravel()).astype(np.int32)   # selection_addgradelower(sel, 0)
 
     def idlistforgrade(self, g):
         return self._ids.get(g, np.zeros(0, dtype=np.int32)).copy()

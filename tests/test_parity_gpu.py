@@ -357,3 +357,43 @@ def test_fd_field_gradient_paths_are_bit_identical(mb):
     finally:
         mb.set_option("fd_elementwise", -1)
         mb.set_option("gradsq_fast_fieldgradient", 1)
+
+
+def _boundary_host(nv, top, sub):
+    """numpy restatement of selection_selectboundary for the checker: facets contained in exactly one top element"""
+    from itertools import combinations
+    k = sub.shape[1]
+
+    def keys(a):
+        out = np.zeros(a.shape[0], dtype=object)
+        for c in range(a.shape[1]):
+            out = out * int(nv) + a[:, c].astype(object)
+        return out
+    cand = np.concatenate([top[:, list(c)] for c in combinations(range(top.shape[1]), k)])
+    uk, cnt = np.unique(keys(cand), return_counts=True)
+    single = set(uk[cnt == 1].tolist())
+    return np.array([i for i, key in enumerate(keys(sub).tolist()) if key in single], dtype=np.int32)
+
+
+def test_boundary_selection_on_device(mb):
+    """Selection(mesh, boundary=true) for surfaces (edges of triangles), volumes (faces of tetrahedra) and lines
+    (end points), against a numpy restatement of selection.c:211-232; a closed surface has no boundary."""
+    from morpho_b200 import meshgen as mg
+    v, f, b = mg.disk(9, 3)
+    m = mb.Mesh(v, faces=f)
+    s = mb.Selection(m, boundary=True)
+    np.testing.assert_array_equal(s.idlistforgrade(1), _boundary_host(m.nv, f, m.addgrade(1)))
+    assert len(s.idlistforgrade(1)) == b.shape[0]
+    np.testing.assert_array_equal(s.idlistforgrade(0), np.unique(b))
+    vs, fs = mg.icosphere(5)
+    assert len(mb.Selection(mb.Mesh(vs, faces=fs), boundary=True).idlistforgrade(1)) == 0
+    vt, t = mg.tet_cube(4)
+    mt = mb.Mesh(vt, volumes=t)
+    st = mb.Selection(mt, boundary=True)
+    faces = mt.addgrade(2)
+    np.testing.assert_array_equal(st.idlistforgrade(2), _boundary_host(mt.nv, t, faces))
+    assert len(st.idlistforgrade(2)) == 6 * 2 * 4 * 4                       # two triangles per boundary cell face
+    vl, e = mg.polyline_loop(12, 3, 3, 0.1)
+    ml = mb.Mesh(vl, edges=e[:-1])                                           # open polyline: two end points
+    assert sorted(mb.Selection(ml, boundary=True).idlistforgrade(0).tolist()) == sorted(
+        [int(i) for i in np.nonzero(np.bincount(e[:-1].ravel(), minlength=12) == 1)[0]])
