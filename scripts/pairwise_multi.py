@@ -25,7 +25,8 @@ mb.init(local)
 L = mb.lib()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 x = torch.from_numpy(mg.sphere_points(n, seed=12345)).cuda()
-b = binbounds(n, world)
+fake = int(os.environ.get("PW_FAKE_WORLD", 0))      # time one rank's block of an N-way partition on a single GPU
+b = binbounds(n, fake if fake else world)
 r0, nr = int(b[rank]), int(b[rank + 1] - b[rank])
 out = torch.zeros(nr * 3, dtype=torch.float64, device="cuda")
 ms = C.c_float()
