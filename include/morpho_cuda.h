@@ -100,7 +100,7 @@ const char *mcu_last_error(void);           /* human readable text of the last f
 const char *mcu_error_id(int status);       /* Morpho error id ("VolEnclZero", …) or "" */
 int mcu_set_option(const char *key, long value);
 long mcu_get_option(const char *key);
-int mcu_sync(void);                         /* wait for the library stream */
+int mcu_sync(void);                         /* wait for the library stream (per-mesh status: mcu_mesh_status) */
 int mcu_set_stream(void *cuda_stream);      /* adopt a caller-owned cudaStream_t (NULL → own stream) */
 
 /* ---- Mesh mirror: object_newmesh (mesh.c:74), Mesh.setvertexmatrix (mesh.c:1145-1160),
@@ -147,6 +147,11 @@ int mcu_selection_get_ids(mcu_selection *s, int *host_ids_sorted, int cap); /* r
  *      returns); mcu_eval_device leaves it in device memory and does not synchronise. ---- */
 int mcu_eval(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *host_out);
 int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *dev_out);
+/* Status contract.  mcu_eval clears the mesh's status word, evaluates, and returns MCU_ERR_DEGENERATE /
+ * MCU_ERR_VOLENCLZERO for THAT evaluation.  mcu_eval_device is asynchronous and cannot: mcu_mesh_status waits for
+ * the stream, then reports and clears whatever the device-path evaluations on this mesh raised since the last
+ * mcu_mesh_status / mcu_eval (a failed evaluation leaves inf/NaN rows; the reference returns nil, functional.c:392). */
+int mcu_mesh_status(mcu_mesh *m);
 /* number of doubles `mode` produces for this functional on this mesh */
 long mcu_result_size(mcu_mesh *m, const mcu_functional *f, int mode);
 

@@ -89,6 +89,7 @@ def lib():
         "mcu_eval": (C.c_int, [vp, C.POINTER(McuFunctional), vp, C.c_int, vp]),
         "mcu_eval_device": (C.c_int, [vp, C.POINTER(McuFunctional), vp, C.c_int, vp]),
         "mcu_result_size": (C.c_long, [vp, C.POINTER(McuFunctional), C.c_int]),
+        "mcu_mesh_status": (C.c_int, [vp]),
         "mcu_pairwise": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_rows_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, C.c_int, C.c_int, vp]),

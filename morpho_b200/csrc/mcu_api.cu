@@ -144,7 +144,7 @@ int mcu_set_stream(void *s) {
     return MCU_OK;
 }
 
-// Wait for the stream and report any status raised by asynchronously launched maps.
+// Wait for the stream.  Status raised by asynchronously launched maps is per mesh: mcu_mesh_status.
 int mcu_sync(void) {
     NEED_INIT();
     CK(cudaStreamSynchronize(g_stream));
@@ -172,7 +172,8 @@ mcu_mesh *mcu_mesh_create(int dim, int nv) {
     return m;
 }
 
-static void conn_free(McuConn &c) {
+static void conn_free(mcu_mesh *m, McuConn &c) {
+    if (c.patches && m->halo) mcu_halo_detach_mesh(m);       // a fused exchange pushed through this patch set
     if (c.d_rix) cudaFree(c.d_rix);
     if (c.d_tptr) cudaFree(c.d_tptr);
     if (c.d_tidx) cudaFree(c.d_tidx);
@@ -183,7 +184,7 @@ static void conn_free(McuConn &c) {
 int mcu_mesh_destroy(mcu_mesh *m) {
     if (!m) return MCU_OK;
     cudaStreamSynchronize(g_stream);
-    for (int g = 0; g < 4; g++) conn_free(m->conn[g]);
+    for (int g = 0; g < 4; g++) conn_free(m, m->conn[g]);
     cudaFree(m->d_vert); cudaFree(m->d_partials); cudaFree(m->d_scalar); cudaFree(m->d_flags);
     if (m->d_result) cudaFree(m->d_result);
     delete m;
@@ -218,7 +219,7 @@ int mcu_mesh_set_connectivity(mcu_mesh *m, int g, int nel, const int *rix) {
     if (!m || g < 1 || g > 3 || g > m->dim || nel < 0 || (nel > 0 && !rix)) { mcu_set_error("bad connectivity arguments"); return MCU_ERR_ARGS; }
     CK(cudaStreamSynchronize(g_stream));
     McuConn &c = m->conn[g];
-    conn_free(c);
+    conn_free(m, c);
     c.g = g; c.nvper = g + 1; c.nel = nel;
     size_t n = (size_t) nel * c.nvper;
     for (size_t i = 0; i < n; i++)
@@ -435,11 +436,15 @@ int mcu_ensure_patches(mcu_mesh *m, int g) {
     if (!m || g != 2 || m->dim != 3 || !m->conn[g].present) return MCU_ERR_UNSUPPORTED;
     McuConn &c = m->conn[g];
     if (c.patches) return MCU_OK;
+    // a refused plan is remembered until the connectivity changes (conn_free resets the flag); planning needs real
+    // coordinates (the bisection works on positions), so not before the first upload
+    if (c.patch_failed || m->vert_version == 0) return MCU_ERR_UNSUPPORTED;
     cudaStream_t st = g_stream;
     CK(cudaStreamSynchronize(st));
     std::vector<double> hv((size_t) m->nv * 3);
     CK(cudaMemcpy(hv.data(), m->d_vert, sizeof(double) * hv.size(), cudaMemcpyDeviceToHost));
     c.patches = mcu_patchset_build(m->nv, c.nel, c.h_rix.data(), hv.data(), st);
+    if (!c.patches) c.patch_failed = true;
     return c.patches ? MCU_OK : MCU_ERR_UNSUPPORTED;
 }
 extern "C" {
@@ -491,9 +496,12 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
 
     if (sel) {
         if (sel->g != g) {
-            // the reference reads sel->selected[g]: a selection holding no ids of this grade selects nothing
-            mcu_set_error("selection grade %d does not match functional grade %d", sel->g, g);
-            return MCU_ERR_ARGS;
+            // the reference reads sel->selected[g] (functional.c:226-229): a selection holding ids of another grade
+            // selects nothing of this one — the total is 0, integrand and gradients are zero matrices
+            long nout = (mode == MCU_TOTAL) ? 1 : (mode == MCU_INTEGRAND ? p.nel : (mode == MCU_GRADIENT ? (long) m->nv * m->dim
+                        : (long) m->nv * f->field[f->wrt]->psize));
+            CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t) nout, g_stream));
+            return MCU_OK;
         }
         int rc = mcu_ensure_selection(sel);
         if (rc) return rc;
@@ -568,6 +576,23 @@ static int check_flags(mcu_mesh *m) {
     return MCU_OK;
 }
 
+static int flags_to_status(unsigned fl) {
+    if (fl & MCU_FLAG_VOLENCLZERO) { mcu_set_error("VolumeEnclosed detected an element of zero size. Check that a mesh point is not coincident with the origin."); return MCU_ERR_VOLENCLZERO; }
+    if (fl & MCU_FLAG_DEGENERATE) { mcu_set_error("degenerate element: the reference returns nil here"); return MCU_ERR_DEGENERATE; }
+    return MCU_OK;
+}
+
+// Status of the asynchronous (mcu_eval_device) evaluations on this mesh since the last mcu_mesh_status / mcu_eval:
+// waits for the stream, reads and clears the status word.
+int mcu_mesh_status(mcu_mesh *m) {
+    NEED_INIT();
+    if (!m) return MCU_ERR_ARGS;
+    int rc = check_flags(m);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_stream));
+    return flags_to_status(*g_hflags);
+}
+
 int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *dev_out) {
     NEED_INIT();
     if (!m || !f || !dev_out) { mcu_set_error("null argument"); return MCU_ERR_ARGS; }
@@ -595,16 +620,15 @@ int mcu_eval(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode,
         }
         d_out = m->d_result;
     }
+    // status raised by earlier mcu_eval_device calls belongs to those (mcu_mesh_status), not to this evaluation
+    CK(cudaMemsetAsync(m->d_flags, 0, sizeof(unsigned), g_stream));
     int rc = eval_impl(m, f, sel, mode, d_out);
     if (rc) return rc;
     if (n > 0) CK(cudaMemcpyAsync(host_out, d_out, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost, g_stream));
     rc = check_flags(m);
     if (rc) return rc;
     CK(cudaStreamSynchronize(g_stream));
-    unsigned fl = *g_hflags;
-    if (fl & MCU_FLAG_VOLENCLZERO) { mcu_set_error("VolumeEnclosed detected an element of zero size. Check that a mesh point is not coincident with the origin."); return MCU_ERR_VOLENCLZERO; }
-    if (fl & MCU_FLAG_DEGENERATE) { mcu_set_error("degenerate element: the reference returns nil here"); return MCU_ERR_DEGENERATE; }
-    return MCU_OK;
+    return flags_to_status(*g_hflags);
 }
 
 /* ------------------------------------------------------------------ Pairwise */

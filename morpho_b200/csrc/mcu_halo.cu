@@ -47,6 +47,9 @@ struct mcu_halo {
     // host copies of the pair lists (for mcu_halo_attach) and the fused mode switch
     std::vector<int> h_shared_local, h_peer_ptr, h_peer_pos;
     bool fused = false;              // pushes ride in the patch gradient kernel; the exchange kernel only combines
+    unsigned pushed_mask = 0;        // fused mode: column blocks (slots) a gradient kernel pushed since the last exchange
+    long long timeout_cycles = 240000000000LL;   // ~2 minutes at 1.9 GHz (option "halo_timeout_ms")
+    bool failed = false;             // a peer timed out in an earlier exchange: reported by the next call
     mcu_mesh *mesh = nullptr;
 };
 
@@ -65,7 +68,7 @@ k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ sha
                 const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
                 const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank, const int *__restrict__ contrib_k,
                 unsigned char *block, size_t recv_off, int rank, int world, int max_m, int ncomp, int parity, int n_pairs,
-                int n_shared, unsigned *counter, unsigned *status, int epoch) {
+                int n_shared, unsigned *counter, unsigned *status, int epoch, long long timeout_cycles) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += gridDim.x * blockDim.x) {
         int q = 0;
         while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
@@ -98,12 +101,13 @@ k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ sha
         for (int q = 0; q < world && good; q++) {
             if (q == rank) continue;
             while (flags[q] < epoch) {
-                if (clock64() - t0 > 4000000000LL) { good = 0; break; }   // ~2 s: a peer is gone; do not hang the GPU
+                if (clock64() - t0 > timeout_cycles) { good = 0; break; }   // a peer is gone; do not hang the GPU
                 __nanosleep(20);
             }
         }
-        // the received rows are read below with cache-bypassing loads (ld.cv) issued after the barrier that follows
-        // this flag observation: no further fence is needed on the acquiring side
+        // acquire side: order the flag observation before the (cache-bypassing, ld.cv) reads of the received rows
+        // that the other threads issue after the barrier below
+        __threadfence_system();
         ok = good;
         if (!good) atomicOr(status, 1u);
     }
@@ -189,6 +193,18 @@ extern "C" int mcu_halo_connect(mcu_halo *h, const unsigned char *handles) {
 extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim) {
     if (!h || ngrad < 1 || ngrad > HALO_MAXGRAD || ngrad * dim > h->ncomp) { mcu_set_error("bad halo exchange arguments"); return MCU_ERR_ARGS; }
     if (h->world == 1) return MCU_OK;
+    if (h->failed) { mcu_set_error("halo exchange: a peer did not arrive in time in an earlier exchange"); return MCU_ERR_CUDA; }
+    // fused mode: the exchange kernel may skip its push phase only when a gradient kernel really pushed every column
+    // block of this exchange (mcu_halo_push_params was taken for slots 0..ngrad-1 since the last exchange).  Any other
+    // route to the gradients (gather path on small meshes, selections, other functionals, a slot out of range, a
+    // patch set freed by mcu_mesh_set_connectivity) leaves rows un-pushed: push them here.
+    const unsigned want = (ngrad >= 32) ? 0xffffffffu : ((1u << ngrad) - 1u);
+    const bool all_pushed = h->fused && (h->pushed_mask & want) == want;
+    h->pushed_mask = 0;
+    {
+        long ms = mcu_opt("halo_timeout_ms", 0);
+        if (ms > 0) h->timeout_cycles = (long long) ms * 2000000LL;
+    }
     HaloGrads g;
     for (int i = 0; i < HALO_MAXGRAD; i++) g.g[i] = i < ngrad ? dev_grads[i] : nullptr;
     cudaStream_t st = mcu_stream();
@@ -199,8 +215,8 @@ extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grad
     nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);             // small enough to be resident as a whole (the CTAs wait for peers)
     k_halo_exchange<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
                                         h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank,
-                                        h->world, h->max_m, h->ncomp, parity, h->fused ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status,
-                                        h->epoch);
+                                        h->world, h->max_m, h->ncomp, parity, all_pushed ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status,
+                                        h->epoch, h->timeout_cycles);
     g_mcu_launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mcu_set_error("halo launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
@@ -213,6 +229,7 @@ extern "C" int mcu_halo_status(mcu_halo *h) {
     unsigned s = 0;
     if (cudaStreamSynchronize(mcu_stream()) != cudaSuccess) return MCU_ERR_CUDA;
     if (cudaMemcpy(&s, h->d_status, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return MCU_ERR_CUDA;
+    if (s) h->failed = true;             // later exchanges fail loudly instead of summing incomplete rows
     return (int) s;
 }
 
@@ -251,7 +268,15 @@ bool mcu_halo_push_params(mcu_halo *h, int slot, int dim, McuHaloPush *out) {
     out->rank = h->rank; out->world = h->world; out->max_m = h->max_m; out->ncomp = h->ncomp;
     out->parity = (h->epoch + 1) & 1;     // the exchange that follows this evaluation
     out->col0 = slot * dim;
+    if (slot < 32) h->pushed_mask |= 1u << slot;
     return true;
+}
+
+// the patch set a fused exchange pushed through is gone (mcu_mesh_set_connectivity / mcu_mesh_destroy)
+void mcu_halo_detach_mesh(mcu_mesh *m) {
+    if (!m || !m->halo) return;
+    m->halo->fused = false; m->halo->mesh = nullptr; m->halo->pushed_mask = 0;
+    m->halo = nullptr;
 }
 
 extern "C" int mcu_halo_destroy(mcu_halo *h) {

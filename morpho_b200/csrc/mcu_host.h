@@ -16,6 +16,7 @@ struct McuConn {
     int *d_rix = nullptr;
     int *d_tptr = nullptr, *d_tidx = nullptr;   // vertex → element transpose (lazily built)
     McuPatchSet *patches = nullptr;  // shared-memory patch decomposition (lazily built, triangles)
+    bool patch_failed = false;       // the planner refused this connectivity: do not plan again until it changes
 };
 
 struct mcu_mesh {
@@ -61,3 +62,4 @@ extern "C" int mcu_ensure_selection(mcu_selection *s);   // uploads ids / transp
 int mcu_ensure_patches(mcu_mesh *m, int g);        // builds conn[g].patches if absent (MCU_ERR_UNSUPPORTED if it cannot)
 struct McuHaloPush;
 bool mcu_halo_push_params(struct mcu_halo *h, int slot, int dim, McuHaloPush *out);
+void mcu_halo_detach_mesh(mcu_mesh *m);

@@ -139,10 +139,11 @@ static mc_mirror *mirror_get(objectmesh *mesh, grade g) {
  * store (field.c:309-327, 1128-1132), which the vertex-matrix hooks do not cover yet; the upload is small next to the
  * finite-difference kernels it feeds. */
 #define MC_MAXFIELDS 32
-typedef struct { objectfield *fld; mc_mirror *owner; mcu_mesh *m; mcu_field *f; int psize, nv; } mc_fieldmirror;
+typedef struct { objectfield *fld; mcu_mesh *m; mcu_field *f; int psize, nv; long used; } mc_fieldmirror;
 static mc_fieldmirror fields[MC_MAXFIELDS];
 static int nfields = 0;
 static long mc_stat_field_uploads = 0;
+static long mc_call_gen = 0;    /* one evaluation = one generation: entries fetched by the current call are never evicted */
 
 static void fields_drop_for(mcu_mesh *m) {
     for (int i = 0; i < nfields;) {
@@ -163,13 +164,23 @@ static mcu_field *field_get(objectfield *fld, mc_mirror *mr) {
     for (int i = 0; i < nfields; i++)
         if (fields[i].fld == fld && fields[i].m == mr->m && fields[i].psize == (int) fld->psize && fields[i].nv == mr->nv) fm = &fields[i];
     if (!fm) {
-        if (nfields == MC_MAXFIELDS) { mcu_field_destroy(fields[0].f); fields[0] = fields[--nfields]; }
+        if (nfields == MC_MAXFIELDS) {
+            /* evict the least recently used entry that the CURRENT evaluation has not fetched (an evaluation holds up
+             * to 16 mcu_field pointers while it fetches the rest) */
+            int victim = -1;
+            for (int i = 0; i < nfields; i++)
+                if (fields[i].used != mc_call_gen && (victim < 0 || fields[i].used < fields[victim].used)) victim = i;
+            if (victim < 0) return NULL;                       /* table full of this call's own fields: reference path */
+            mcu_field_destroy(fields[victim].f);
+            fields[victim] = fields[--nfields];
+        }
         fm = &fields[nfields];
         fm->f = mcu_field_create(mr->m, (int) fld->psize);
         if (!fm->f) return NULL;
-        fm->fld = fld; fm->m = mr->m; fm->owner = mr; fm->psize = (int) fld->psize; fm->nv = mr->nv;
+        fm->fld = fld; fm->m = mr->m; fm->psize = (int) fld->psize; fm->nv = mr->nv;
         nfields++;
     }
+    fm->used = mc_call_gen;
     if (mcu_field_set(fm->f, fld->data.elements) != MCU_OK) return NULL;
     mc_stat_field_uploads++;
     return fm->f;
@@ -268,6 +279,7 @@ static bool prop(objectinstance *self, const char *name, value *out) {
 
 static bool mc_eval_props(vm *v, int nargs, value *args, int functional, int mode, value *out) {
     functional_mapinfo info;
+    mc_call_gen++;
     *out = MORPHO_NIL;
     if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
     if (!functional_validateargs(v, nargs, args, &info)) return true;
@@ -405,6 +417,7 @@ MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, gradient, MCU_GRADIENT)
 static long mc_stat_translated = 0;
 static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, value *out) {
     functional_mapinfo info;
+    mc_call_gen++;
     *out = MORPHO_NIL;
     if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
     if (!functional_validateargs(v, nargs, args, &info)) return true;

@@ -39,8 +39,3 @@ def reference():
 def cases():
     from tests.golden.cases import all_cases
     return all_cases()
-
-
-def run_backend(backend, case, ev, gold_selorder=None):
-    """Evaluate one case entry on `backend` ('oracle' object or the CUDA package)."""
-    raise NotImplementedError
