@@ -192,9 +192,18 @@ int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
  *      potential like functional_mapnumericalgradient does when no gradient function was supplied. ---- */
 int mcu_pointwise(mcu_mesh *m, int nprog, const int *nops, const mcu_expr_op *progs, mcu_selection *sel, int mode, double *host_out);
 
-/* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.
- *      kind 0: Coulomb f=1/r, f'=-1/r^2 (examples/thomson/thomson.morpho:26).
+/* ---- PairwisePotential (modules/functionals.morpho:87-141), all-pairs FP64.  The reference takes two Morpho closures,
+ *      func(r) and grad(r) = func'(r); here the potential is one of these families (the extension recognises them from
+ *      the closures' bytecode, anything else arrives as a pair of postfix programs):
+ *        MCU_PW_COULOMB  f = a/r                        params = {a}           (NULL: a = 1; examples/thomson/thomson.morpho:26)
+ *        MCU_PW_LAURENT  f = sum_t a_t r^k_t, k_t integer  params = {nt, a_0, k_0, a_1, k_1, ...}, nt <= 6
+ *                        (power laws, Lennard-Jones 4e((s/r)^12 - (s/r)^6) = {2, 4 e s^12, -12, -4 e s^6, -6}); f' is derived
+ *        MCU_PW_YUKAWA   f = a exp(-r/l)/r              params = {a, l}
+ *        MCU_PW_PROGRAM  f and f' as postfix programs over r (MCU_X_POS a = 0), set by mcu_pairwise_program
+ *      cutoff > 0: pairs with r > cutoff are skipped (functionals.morpho:113,130).
  *      mode MCU_TOTAL / MCU_INTEGRAND (n doubles) / MCU_GRADIENT (n*dim doubles). ---- */
+enum { MCU_PW_COULOMB = 0, MCU_PW_LAURENT = 1, MCU_PW_YUKAWA = 2, MCU_PW_PROGRAM = 3 };
+int mcu_pairwise_program(int nops_f, const mcu_expr_op *prog_f, int nops_g, const mcu_expr_op *prog_g);
 int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *params, double cutoff,
                  int mode, double *host_out);
 int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff,

@@ -15,6 +15,7 @@ MCU_OK, MCU_ERR_ARGS, MCU_ERR_ELNOTFOUND, MCU_ERR_DEGENERATE, MCU_ERR_VOLENCLZER
     MCU_ERR_UNSUPPORTED, MCU_ERR_CUDA, MCU_ERR_ALLOC = range(8)
 MCU_TOTAL, MCU_INTEGRAND, MCU_GRADIENT, MCU_FIELDGRADIENT = range(4)
 MCU_PATH_AUTO, MCU_PATH_GATHER, MCU_PATH_PATCH = range(3)
+MCU_PW_COULOMB, MCU_PW_LAURENT, MCU_PW_YUKAWA, MCU_PW_PROGRAM = range(4)
 
 FUNCTIONAL_IDS = {
     "Length": 1, "AreaEnclosed": 2, "Area": 3, "VolumeEnclosed": 4, "Volume": 5,
@@ -90,6 +91,7 @@ def lib():
         "mcu_eval_device": (C.c_int, [vp, C.POINTER(McuFunctional), vp, C.c_int, vp]),
         "mcu_result_size": (C.c_long, [vp, C.POINTER(McuFunctional), C.c_int]),
         "mcu_mesh_status": (C.c_int, [vp]),
+        "mcu_pairwise_program": (C.c_int, [C.c_int, vp, C.c_int, vp]),
         "mcu_pairwise": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_rows_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, C.c_int, C.c_int, vp]),

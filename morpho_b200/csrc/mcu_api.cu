@@ -635,13 +635,14 @@ int mcu_eval(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode,
 
 int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff, int mode, double *dev_out) {
     NEED_INIT();
-    (void) params;
-    if (n < 0 || (dim != 2 && dim != 3) || !dev_x || !dev_out || kind != 0) { mcu_set_error("bad pairwise arguments"); return MCU_ERR_ARGS; }
+    if (n < 0 || (dim != 2 && dim != 3) || !dev_x || !dev_out) { mcu_set_error("bad pairwise arguments"); return MCU_ERR_ARGS; }
     static CompSum *partials = nullptr;
     if (!partials) CK(cudaMalloc((void **) &partials, sizeof(CompSum) * 4096));
-    cudaError_t e = mcu_pairwise_launch(n, dim, dev_x, kind, cutoff, mode, dev_out, partials, g_stream);
+    int status = MCU_OK;
+    cudaError_t e = mcu_pairwise_launch(n, dim, dev_x, kind, params, cutoff, mode, dev_out, partials, g_stream, 0, -1, &status);
     if (e != cudaSuccess) { mcu_set_error("pairwise launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
-    return MCU_OK;
+    if (status) mcu_set_error("bad pairwise potential (kind %d)", kind);
+    return status;
 }
 
 /* rows [row0, row0 + nrows) of the all-pairs interaction: the block one GPU computes when the N x N matrix is
@@ -650,13 +651,14 @@ int mcu_pairwise_device(int n, int dim, const double *dev_x, int kind, const dou
 int mcu_pairwise_rows_device(int n, int dim, const double *dev_x, int kind, const double *params, double cutoff, int mode,
                              int row0, int nrows, double *dev_out) {
     NEED_INIT();
-    (void) params;
-    if (n < 0 || (dim != 2 && dim != 3) || !dev_x || !dev_out || kind != 0 || row0 < 0 || nrows < 0 || row0 + nrows > n) { mcu_set_error("bad pairwise arguments"); return MCU_ERR_ARGS; }
+    if (n < 0 || (dim != 2 && dim != 3) || !dev_x || !dev_out || row0 < 0 || nrows < 0 || row0 + nrows > n) { mcu_set_error("bad pairwise arguments"); return MCU_ERR_ARGS; }
     static CompSum *partials = nullptr;
     if (!partials) CK(cudaMalloc((void **) &partials, sizeof(CompSum) * 4096));
-    cudaError_t e = mcu_pairwise_launch(n, dim, dev_x, kind, cutoff, mode, dev_out, partials, g_stream, row0, nrows);
+    int status = MCU_OK;
+    cudaError_t e = mcu_pairwise_launch(n, dim, dev_x, kind, params, cutoff, mode, dev_out, partials, g_stream, row0, nrows, &status);
     if (e != cudaSuccess) { mcu_set_error("pairwise launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
-    return MCU_OK;
+    if (status) mcu_set_error("bad pairwise potential (kind %d)", kind);
+    return status;
 }
 
 int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *params, double cutoff, int mode, double *host_out) {
@@ -674,6 +676,12 @@ int mcu_pairwise(int n, int dim, const double *host_x, int kind, const double *p
         if (e != cudaSuccess) { mcu_set_error("pairwise copy failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
     }
     cudaFree(d_x); cudaFree(d_out);
+    return rc;
+}
+
+int mcu_pairwise_program(int nops_f, const mcu_expr_op *prog_f, int nops_g, const mcu_expr_op *prog_g) {
+    int rc = mcu_pairwise_store_program(nops_f, prog_f, nops_g, prog_g);
+    if (rc) mcu_set_error("pairwise program rejected (unsupported op, unbalanced stack, or longer than 64 ops)");
     return rc;
 }
 

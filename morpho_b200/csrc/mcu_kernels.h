@@ -25,5 +25,6 @@ cudaError_t mcu_patch_total(int functional, const McuPatchSet &ps, const double 
 int mcu_patchset_attach_push(McuPatchSet *ps, int nv, int n, const int *vertex, const int *peer, const int *k, cudaStream_t st);
 
 // All-pairs kernels.
-cudaError_t mcu_pairwise_launch(int n, int dim, const double *d_x, int kind, double cutoff, int mode,
-                                double *d_out, CompSum *partials, cudaStream_t st, int row0 = 0, int nrows = -1);
+cudaError_t mcu_pairwise_launch(int n, int dim, const double *d_x, int kind, const double *params, double cutoff, int mode,
+                                double *d_out, CompSum *partials, cudaStream_t st, int row0 = 0, int nrows = -1, int *status = nullptr);
+int mcu_pairwise_store_program(int nf, const mcu_expr_op *pf, int ng, const mcu_expr_op *pg);

@@ -189,19 +189,47 @@ class NematicElectric(_FieldFunctional):
 class PairwisePotential:
     """All-pairs potential on the mesh vertices (modules/functionals.morpho:87-141).
 
-    Only closures the device knows can be accelerated; ``kind="coulomb"`` is
-    f(r) = 1/r, f'(r) = -1/r^2, the pair used by examples/thomson/thomson.morpho:26.
+    The reference takes two closures ``func(r)``, ``grad(r)``.  Here the potential is named (the extension derives the
+    same description from the closures' bytecode):
+
+    * ``kind="coulomb", a=1``           f = a/r  (examples/thomson/thomson.morpho:26)
+    * ``kind="power", a, p``            f = a r^-p  (integer p)
+    * ``kind="laurent", terms=[(a,k)]`` f = sum a r^k  (integer k)
+    * ``kind="lj", eps, sigma``         f = 4 eps ((sigma/r)^12 - (sigma/r)^6)
+    * ``kind="yukawa", a, l``           f = a exp(-r/l)/r
+    * ``kind="program", func, grad``    callables of r written with :mod:`morpho_b200.integrand` operators
     """
 
-    def __init__(self, kind="coulomb", cutoff=None):
-        if kind != "coulomb":
+    def __init__(self, kind="coulomb", cutoff=None, **kw):
+        self.cutoff = 0.0 if cutoff is None else float(cutoff)
+        self._progs = None
+        if kind == "coulomb":
+            self.kind, self.params = _lib.MCU_PW_COULOMB, [float(kw.get("a", 1.0))]
+        elif kind == "power":
+            self.kind, self.params = _lib.MCU_PW_LAURENT, [1.0, float(kw["a"]), -float(int(kw["p"]))]
+        elif kind == "laurent":
+            t = list(kw["terms"])
+            self.kind, self.params = _lib.MCU_PW_LAURENT, [float(len(t))] + [float(v) for ak in t for v in ak]
+        elif kind == "lj":
+            e, sg = float(kw["eps"]), float(kw["sigma"])
+            self.kind, self.params = _lib.MCU_PW_LAURENT, [2.0, 4 * e * sg ** 12, -12.0, -4 * e * sg ** 6, -6.0]
+        elif kind == "yukawa":
+            self.kind, self.params = _lib.MCU_PW_YUKAWA, [float(kw["a"]), float(kw["l"])]
+        elif kind == "program":
+            from .integrand import trace
+            self.kind, self.params = _lib.MCU_PW_PROGRAM, [0.0]
+            self._progs = (trace(lambda x: kw["func"](x[0]), 1, []), trace(lambda x: kw["grad"](x[0]), 1, []))
+        else:
             raise MorphoError(_lib.MCU_ERR_UNSUPPORTED, "", f"pairwise kind '{kind}' is not accelerated")
-        self.kind, self.cutoff = 0, (0.0 if cutoff is None else float(cutoff))
 
     def _run(self, mesh, mode, n):
         out = np.zeros(max(n, 1))
         x = mesh._vert
-        check(lib().mcu_pairwise(mesh.nv, mesh.dim, x.ctypes.data, self.kind, None, self.cutoff, mode, out.ctypes.data))
+        if self._progs is not None:
+            pf, pg = self._progs
+            check(lib().mcu_pairwise_program(len(pf), pf.ctypes.data, len(pg), pg.ctypes.data))
+        p = np.ascontiguousarray(self.params, dtype=np.float64)
+        check(lib().mcu_pairwise(mesh.nv, mesh.dim, x.ctypes.data, self.kind, p.ctypes.data, self.cutoff, mode, out.ctypes.data))
         return out[:n]
 
     def integrand(self, mesh):

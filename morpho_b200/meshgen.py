@@ -275,3 +275,4 @@ def write_mesh_file(path, vert, **grades):
             fh.write(f"\n{names[g]}\n\n")
             for i, el in enumerate(conn):
                 fh.write(f"{i + 1} " + " ".join(str(int(c) + 1) for c in el) + "\n")
+        fh.write("\n")      # the reference's loader repeats the last entry of a file that ends without a blank line

@@ -665,7 +665,30 @@ void mo_binbounds(int nel, int nbins, int *bounds) {
  * Matrix arithmetic of the script: dx = x_i - x_j (matrix sub), r = dx.norm()
  * (dnrm2), out[i] += 0.5*f ; gradient: df = grad(r)/r ; column_i = df*dx + column_i.
  * ------------------------------------------------------------------ */
-int mo_pairwise_coulomb_integrand(int n, int dim, const double *x, double cutoff, double *out) {
+/* The closures func(r) / grad(r) a script hands to PairwisePotential, for the potential families the library knows
+ * (include/morpho_cuda.h MCU_PW_*), written as the closures of tests/golden/pairwise_cases.py write them
+ * (Morpho's ^ is pow(), veneer.c / vm.c OP_POW). */
+static double pw_func(int kind, const double *p, double r) {
+    switch (kind) {
+        case 0: return p[0] / r;                                         /* fn (r) a/r */
+        case 1: return p[0] / pow(r, p[1]);                              /* fn (r) a/r^p */
+        case 2: return p[0] * exp(-r / p[1]) / r;                        /* fn (r) a*exp(-r/l)/r */
+        case 3: return 4 * p[0] * (pow(p[1] / r, 12) - pow(p[1] / r, 6)); /* fn (r) 4 e ((s/r)^12-(s/r)^6) */
+    }
+    return NAN;
+}
+static double pw_grad(int kind, const double *p, double r) {
+    switch (kind) {
+        case 0: return -p[0] / pow(r, 2);
+        case 1: return -p[0] * p[1] / pow(r, p[1] + 1);
+        case 2: return -p[0] * exp(-r / p[1]) * (1 / pow(r, 2) + 1 / (p[1] * r));
+        case 3: return 4 * p[0] * (-12 * pow(p[1] / r, 12) + 6 * pow(p[1] / r, 6)) / r;
+    }
+    return NAN;
+}
+
+/* PairwisePotential.integrand (functionals.morpho:105-121) */
+int mo_pairwise_integrand(int n, int dim, const double *x, int kind, const double *params, double cutoff, double *out) {
     memset(out, 0, sizeof(double) * (size_t) n);
     for (int i = 0; i < n; i++)
         for (int j = i + 1; j < n; j++) {
@@ -673,14 +696,15 @@ int mo_pairwise_coulomb_integrand(int n, int dim, const double *x, double cutoff
             vecsub(dim, x + (size_t) i * dim, x + (size_t) j * dim, dx);
             double r = vecnorm(dim, dx);
             if (cutoff > 0 && r > cutoff) continue;
-            double fv = 1 / r;
+            double fv = pw_func(kind, params, r);
             out[i] += 0.5 * fv;
             out[j] += 0.5 * fv;
         }
     return MO_OK;
 }
 
-int mo_pairwise_coulomb_gradient(int n, int dim, const double *x, double cutoff, double *out) {
+/* PairwisePotential.gradient (functionals.morpho:123-139) */
+int mo_pairwise_gradient(int n, int dim, const double *x, int kind, const double *params, double cutoff, double *out) {
     memset(out, 0, sizeof(double) * (size_t) n * dim);
     for (int i = 0; i < n; i++)
         for (int j = i + 1; j < n; j++) {
@@ -688,11 +712,30 @@ int mo_pairwise_coulomb_gradient(int n, int dim, const double *x, double cutoff,
             vecsub(dim, x + (size_t) i * dim, x + (size_t) j * dim, dx);
             double r = vecnorm(dim, dx);
             if (cutoff > 0 && r > cutoff) continue;
-            double df = (-1 / (r * r)) / r; /* grad(r)/r with grad(r) = -1/r^2 */
+            double df = pw_grad(kind, params, r) / r;
             for (int k = 0; k < dim; k++) {
                 out[(size_t) i * dim + k] = df * dx[k] + out[(size_t) i * dim + k];
                 out[(size_t) j * dim + k] = -df * dx[k] + out[(size_t) j * dim + k];
             }
         }
     return MO_OK;
+}
+
+/* Functional.total (functionals.morpho:50-53): integrand(mesh).sum() — Matrix.sum is a Kahan sum (matrix.c matrix_sum) */
+double mo_pairwise_total(int n, int dim, const double *x, int kind, const double *params, double cutoff) {
+    double *e = malloc(sizeof(double) * (size_t) (n > 0 ? n : 1));
+    mo_pairwise_integrand(n, dim, x, kind, params, cutoff, e);
+    double sum = 0.0, c = 0.0;
+    for (int i = 0; i < n; i++) { double y = e[i] - c, t = sum + y; c = (t - sum) - y; sum = t; }
+    free(e);
+    return sum;
+}
+
+int mo_pairwise_coulomb_integrand(int n, int dim, const double *x, double cutoff, double *out) {
+    const double one = 1.0;
+    return mo_pairwise_integrand(n, dim, x, 0, &one, cutoff, out);
+}
+int mo_pairwise_coulomb_gradient(int n, int dim, const double *x, double cutoff, double *out) {
+    const double one = 1.0;
+    return mo_pairwise_gradient(n, dim, x, 0, &one, cutoff, out);
 }

@@ -96,6 +96,10 @@ int mo_edges_from(int nel, int nvper, const int *conn, int *edges_out /* cap nel
 
 /* PairwisePotential with Coulomb closures f(r)=1/r, f'(r)=-1/r^2
  * (modules/functionals.morpho:105-139; examples/thomson/thomson.morpho:26). */
+/* kind / params: include/morpho_cuda.h MCU_PW_* (0 Coulomb [a], 1 power law [a,p], 2 Yukawa [a,l], 3 Lennard-Jones [e,s]) */
+int mo_pairwise_integrand(int n, int dim, const double *x, int kind, const double *params, double cutoff, double *out /* n */);
+int mo_pairwise_gradient(int n, int dim, const double *x, int kind, const double *params, double cutoff, double *out /* n*dim */);
+double mo_pairwise_total(int n, int dim, const double *x, int kind, const double *params, double cutoff);
 int mo_pairwise_coulomb_integrand(int n, int dim, const double *x, double cutoff, double *out /* n */);
 int mo_pairwise_coulomb_gradient(int n, int dim, const double *x, double cutoff, double *out /* n*dim */);
 

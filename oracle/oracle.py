@@ -89,6 +89,10 @@ class Oracle:
         L.mo_binbounds.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
         for fn in ("mo_pairwise_coulomb_integrand", "mo_pairwise_coulomb_gradient"):
             getattr(L, fn).argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+        for fn in ("mo_pairwise_integrand", "mo_pairwise_gradient"):
+            getattr(L, fn).argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+        L.mo_pairwise_total.restype = C.c_double
+        L.mo_pairwise_total.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_double]
 
     # -- helpers ---------------------------------------------------------------
     @staticmethod
@@ -184,6 +188,21 @@ class Oracle:
         b = np.zeros(nbins + 1, dtype=np.int32)
         self.lib.mo_binbounds(nel, nbins, _iptr(b))
         return b
+
+    def pairwise(self, x, mode, kind=0, params=(1.0,), cutoff=0.0):
+        """PairwisePotential (modules/functionals.morpho:87-141) for the closure families of tests/golden/pairwise_cases.py."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, dim = x.shape
+        p = np.ascontiguousarray(list(params) + [0.0] * 4, dtype=np.float64)
+        if mode == "total":
+            return float(self.lib.mo_pairwise_total(n, dim, _dptr(x), kind, _dptr(p), cutoff))
+        if mode == "integrand":
+            out = np.zeros(n)
+            self.lib.mo_pairwise_integrand(n, dim, _dptr(x), kind, _dptr(p), cutoff, _dptr(out))
+        else:
+            out = np.zeros((n, dim))
+            self.lib.mo_pairwise_gradient(n, dim, _dptr(x), kind, _dptr(p), cutoff, _dptr(out))
+        return out
 
     def pairwise_coulomb(self, x, mode, cutoff=0.0):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -189,6 +189,27 @@ def test_pairwise_against_oracle(mb, oracle):
     assert rel_array(pc.gradient(m), oracle.pairwise_coulomb(x, "gradient", 0.5), rows=3) <= TOL_EXACT
 
 
+def test_pairwise_against_the_interpreted_reference(mb):
+    """tests/golden/pairwise.npz: the reference's interpreted PairwisePotential (modules/functionals.morpho:87-141, real
+    closures, run by oracle/_ref/morpho6) at N = 500 / 1000 / 2000 and for power-law, Yukawa, Lennard-Jones, cut-off and
+    2-D cases — against every library route to the same potential (named family and postfix programs)."""
+    from tests.golden.pairwise_cases import CASES as PW, LIB
+    from tests.parity import rel_scalar
+    G = np.load(os.path.join(GOLD, "pairwise.npz"))
+    worst = {}
+    for name, n, *_ in PW:
+        x = G[name + "__x"]
+        m = mb.Mesh(x)
+        for kw in LIB[name]:
+            p = mb.PairwisePotential(**kw)
+            e = rel_array(p.integrand(m), G[name + "__integrand"])
+            g = rel_array(p.gradient(m), G[name + "__gradient"], rows=x.shape[1])
+            t = rel_scalar(p.total(m), float(G[name + "__total"][0]))
+            worst[f"{name}/{kw['kind']}"] = max(e, g, t)
+            assert max(e, g, t) <= TOL_EXACT, (name, kw["kind"], e, g, t)
+    print("pairwise vs interpreted reference, worst relative error per route:", {k: f"{v:.1e}" for k, v in worst.items()})
+
+
 def test_full_size_properties(mb, oracle):
     """BASELINE.json config 2 at full size (icosphere f=707: 9 996 980 triangles).  Size-independent
     properties: Area is homogeneous of degree 2 and VolumeEnclosed of degree 3 in the coordinates
