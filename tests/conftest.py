@@ -39,3 +39,19 @@ def reference():
 def cases():
     from tests.golden.cases import all_cases
     return all_cases()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Worst achieved parity errors of this session (tests/parity.py record()) → gpurun_out/parity_errors.json."""
+    import json
+    from tests import parity
+    rec = parity.recorded()
+    if not rec:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as fh:
+            json.dump({g: {str(k): v for k, v in sorted(d.items(), key=lambda kv: str(kv[0]))} for g, d in rec.items()}, fh, indent=1)
+    except OSError:
+        pass

@@ -155,6 +155,44 @@ def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
         assert fallbacks == 0 and field_uploads > 0, stats       # every call of the script ran on the GPU
 
 
+EXAMPLES = os.path.join(REF, "examples")
+PLOT_LINE = re.compile(r"^\s*(import\s+plot\b|var\s+g\s*=\s*plot|g\s*=\s*plot|g\.title\b|Show\s*\()")
+
+
+def shipped_example(path, tail):
+    """An example of the reference AS SHIPPED (oracle/_ref/examples, copied by build_ref.sh): only the lines that open
+    the plot viewer (`import plot`, plotselection/plotmesh, g.title, Show) are dropped — there is no display — and
+    `tail` (prints at full precision) is appended.  Nothing else of the script is touched."""
+    keep = [l for l in open(path).read().splitlines() if not PLOT_LINE.match(l)]
+    return "\n".join(keep) + "\n" + tail + "\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="oracle/_ref/examples not built")
+def test_catenoid_example_as_shipped(tmp_path):
+    """BASELINE.json config 1 / SURVEY 8d: examples/catenoid/catenoid.morpho unchanged (AreaMesh 20 x 6, boundary fixed,
+    conjugategradient(1000)), stock reference against `import morphocuda`: the same number of iterations and the
+    energy after EVERY iteration (opt.energy, printed with 17 digits) equal to <= 1e-12 relative."""
+    tail = 'print "history ${opt.energy.count()}"\nfor (e in opt.energy) print e.format("%.17g")\nprint area.total(mesh).format("%.17g")'
+    src = shipped_example(os.path.join(EXAMPLES, "catenoid", "catenoid.morpho"), tail)
+    assert "conjugategradient(1000)" in src and "import plot" not in src
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    assert "ready:" in err, err
+    stats = [int(x) for x in NUM.findall(new[-1])]
+    assert stats[0] > 20 and stats[3] == 0, stats                 # evaluations on the GPU, none left to the reference
+    i = ref.index([l for l in ref if l.startswith("history")][0])
+    assert ref[i] == new[i], (ref[i], new[i])                      # same number of iterations
+    hr, hn = [float(x) for x in ref[i + 1:]], [float(x) for x in new[i + 1:-1]]
+    assert len(hr) == len(hn) >= 10
+    worst = max(abs(a - b) / abs(a) for a, b in zip(hr, hn))
+    from tests.parity import record
+    record("extension", "catenoid_as_shipped.energy_history", worst)
+    print(f"catenoid as shipped: {len(hr) - 1} iterations, final energy {hn[-1]:.12g}, worst per-iteration relative difference {worst:.2e}")
+    assert worst <= 1e-12, worst
+    compare(ref[:i], new[:i], 1e-5)                                # the report lines print 6 significant digits
+
+
 @pytest.mark.gpu
 def test_paranoid_mode_matches_hooked_mode(tmp_path):
     src = "import morphocuda\n" + script("functionals_basic.morpho")
