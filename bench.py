@@ -46,6 +46,17 @@ def frequency_for(ngpu: int, base: int) -> int:
     return int(round(base * np.sqrt(ngpu)))
 
 
+def workload_string(f: int, world: int) -> str:
+    """The same text in both arms (the driver compares the arms' `config.workload`)."""
+    nel, nv = 20 * f * f, 10 * f * f + 2
+    per = -(-nel // world)
+    return (f"icosphere f={f} ({nel} triangles, {nv} vertices global; {per} triangles per GPU on {world} GPU(s)), radial perturbation 1%, "
+            "seed 12345; step = Area.gradient + VolumeEnclosed.gradient (2 element-evals per triangle)")
+
+
+INPUTS = "larger than L2 (vertex matrix 120 MB + ring tables 101 MB + gradient 120 MB per functional, per GPU)"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -128,13 +139,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from morpho_b200 import meshgen as mg
-    f = args.freq
+    from morpho_b200.partition import build_rank_mesh
+    world = max(int(args.gpus), 1)
+    f = frequency_for(world, args.freq)
     t0 = time.time()
-    vert, conn = mg.icosphere(f)
-    vert = mg.perturb_radially(vert)
+    part = build_rank_mesh(f, 0, 1) if world == 1 else _rank0_range(f, world)
+    vert, conn = part.vert, part.conn
     nel = conn.shape[0]
-    log(f"[reference] mesh f={f}: {nel} triangles built in {time.time() - t0:.1f}s")
+    log(f"[reference] mesh f={f}: rank 0's {nel} of {part.nel_global} triangles built in {time.time() - t0:.1f}s")
     ncores = os.cpu_count() or 1
     # calibrate on 1M triangles.  "All the host threads it can use": the reference's threaded map does not always
     # win (per-thread full gradient matrices + serial merge, functional.c:1092-1135), so keep the faster setting.
@@ -156,19 +168,33 @@ def run_reference(args):
     ts = reference_steps(vs, cs, args.steps, args.warmup, threads)
     sec = float(np.mean(ts))
     value = 2.0 * m / sec / 1e6
-    sample = (f"first {m} of {nel} triangles per step ({'the whole mesh' if m == nel else 'bounded sample'}), {args.steps} steps; "
+    sample = (f"first {m} of {part.nel_global} triangles per step ({'the whole mesh' if m == part.nel_global else 'bounded sample'}), {args.steps} steps; "
               f"threads={threads} (0 = the reference's serial default path), the faster of serial and {ncores} threads; OPENBLAS_NUM_THREADS=1")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"icosphere f={f} ({nel} triangles, {vert.shape[0]} vertices), radial perturbation 1%, seed 12345; "
-                               "step = Area.gradient + VolumeEnclosed.gradient (2 element-evals per triangle)", "inputs": "larger than L2"},
+        "config": {"workload": workload_string(f, world), "inputs": INPUTS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": max(threads, 1), "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _rank0_range(f, world):
+    """Rank 0's contiguous element range of the N-GPU workload, built without torch.distributed (no shared-vertex lists)."""
+    from morpho_b200 import meshgen as mg
+    from morpho_b200.partition import RankMesh, binbounds
+    topo = mg.IcoTopology(f)
+    hi = int(binbounds(topo.nel, world)[1])
+    tpf = topo.tri_per_face
+    parts = [topo.face_triangles(fi)[: min(hi - fi * tpf, tpf)] for fi in range((hi - 1) // tpf + 1)]
+    cg = np.concatenate(parts)
+    gids = np.unique(cg)
+    vert = topo.positions(gids) * mg.radial_factors(topo.nv, 0.01, 12345)[gids][:, None]
+    conn = np.sort(np.searchsorted(gids, cg).astype(np.int32), axis=1)
+    return RankMesh(0, world, topo.nel, topo.nv, (0, hi), gids.astype(np.int64), np.ascontiguousarray(vert), np.ascontiguousarray(conn))
 
 
 def cpu_baseline_sample(vert, conn):
@@ -195,6 +221,68 @@ def cpu_baseline_sample(vert, conn):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+
+def parity_check(part, vert, conn, step_device, g_area, g_vol, torch, dist, world, rank, barrier, nsample=10_000):
+    """Before anything is timed: one step on the device, then this rank's COMPLETED gradient rows — every row of a
+    vertex shared with another rank plus `nsample` seeded interior rows — against the CPU oracle
+    (oracle/morpho_oracle.c, the restatement of functional_mapgradient + area/volumeenclosed gradients that
+    tests/test_oracle_golden.py pins to the unmodified reference).  The oracle evaluates this rank's element range;
+    the rows of shared vertices are completed on the host the way the reference merges its per-thread matrices
+    (functional.c:1106-1119): partial rows all-gathered and added in ascending rank order.  Returns the max over ranks
+    of the global measure max_v|d|/max_v|g| and of the per-vertex measure of tests/parity.py, and whether all ranks
+    that share a vertex hold bitwise identical rows."""
+    from oracle.oracle import FunctionalSpec, Oracle
+    from tests.parity import contribution_norm_sum, EPS_FLOOR
+    O = Oracle()
+    step_device()
+    barrier()
+    dim = vert.shape[1]
+    got = [g_area.cpu().numpy().reshape(-1, dim), g_vol.cpu().numpy().reshape(-1, dim)]
+    want = [O.gradient(vert, {2: conn}, FunctionalSpec(n)) for n in ("Area", "VolumeEnclosed")]
+    S = [contribution_norm_sum(n, vert, conn) for n in ("Area", "VolumeEnclosed")]
+    bitwise = True
+    sl, ss, ns = part.shared_local, part.shared_slot, part.n_slots
+    if world > 1 and ns > 0:
+        # oracle side: complete the shared rows (and their contribution sums) in ascending rank order
+        buf = np.zeros((ns, 2 * dim + 2))
+        buf[ss, :dim], buf[ss, dim:2 * dim] = want[0][sl], want[1][sl]
+        buf[ss, 2 * dim], buf[ss, 2 * dim + 1] = S[0][sl], S[1][sl]
+        t = torch.from_numpy(buf).cuda()
+        allb = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allb, t)
+        tot = allb[0].cpu().numpy().copy()
+        for r in range(1, world):
+            tot += allb[r].cpu().numpy()
+        want[0][sl], want[1][sl] = tot[ss, :dim], tot[ss, dim:2 * dim]
+        S[0][sl], S[1][sl] = tot[ss, 2 * dim], tot[ss, 2 * dim + 1]
+        # device side: every rank that holds a shared vertex must hold the same bits
+        mine = np.zeros((ns, 2 * dim + 1))
+        mine[ss, :dim], mine[ss, dim:2 * dim], mine[ss, 2 * dim] = got[0][sl], got[1][sl], 1.0
+        t = torch.from_numpy(mine).cuda()
+        allm = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allm, t)
+        allm = [a.cpu().numpy() for a in allm]
+        for r in range(world):
+            both = (allm[r][:, 2 * dim] > 0) & (mine[:, 2 * dim] > 0)
+            if not np.array_equal(allm[r][both, :2 * dim].view(np.int64), mine[both, :2 * dim].view(np.int64)):
+                bitwise = False
+    rng = np.random.Generator(np.random.PCG64(4321 + rank))
+    rows = np.unique(np.concatenate([sl, rng.integers(0, vert.shape[0], size=min(nsample, vert.shape[0]))])).astype(np.int64)
+    worst = worst_pv = 0.0
+    for a, b, s_ in zip(got, want, S):
+        num = np.linalg.norm(a[rows] - b[rows], axis=1)
+        scale = np.linalg.norm(b, axis=1).max()
+        worst = max(worst, float(num.max() / scale))
+        den = np.maximum(np.linalg.norm(b[rows], axis=1), EPS_FLOOR * s_[rows])
+        worst_pv = max(worst_pv, float((num[den > 0] / den[den > 0]).max()))
+    res = torch.tensor([worst, worst_pv, 0.0 if bitwise else 1.0, float(len(rows))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    res = res.cpu().numpy()
+    return {"max_rel": float(res[0]), "max_rel_pervertex": float(res[1]), "shared_rows_bitwise_equal": bool(res[2] == 0.0),
+            "rows_checked_per_rank": int(res[3]), "shared_rows": int(len(sl)), "against": "oracle/morpho_oracle.c (pinned to the unmodified reference)",
+            "tolerance": 1e-12}
+
 
 def run_ours(args):
     import torch
@@ -268,6 +356,15 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity of what is about to be timed (checker only: the CPU oracle, never the thing measured) ------
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(part, vert, conn, step_device, g_area, g_vol, torch, dist, world, rank, barrier)
+        if rank == 0:
+            log(f"[parity] {parity}")
+        if parity["max_rel"] > 1e-12 or parity["max_rel_pervertex"] > 1e-12 or not parity["shared_rows_bitwise_equal"]:
+            raise SystemExit(f"parity check failed: {parity}")
 
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -367,20 +464,24 @@ def run_ours(args):
     kname = "k_patch_ring"
     ms_dom, dom = (ms_area, kname + "<Area>") if ms_area >= ms_vol else (ms_vol, kname + "<VolumeEnclosed>")
     achieved = BYTES_PER_ELEM_GRADIENT * nel_local / (ms_dom * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch cannot be measured outside a profiler: the figure is the one of the committed
+    # `ncu --set full` capture, and it is only reported while the kernel source is byte-identical to the captured one
+    traffic, traffic_note = None, "no ncu capture of the current kernel source"
     tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            import hashlib
+            rec = json.load(open(tp))
+            sha = hashlib.sha256(open(os.path.join(ROOT, "morpho_b200", "csrc", "mcu_patch.cu"), "rb").read()).hexdigest()[:16]
+            if rec.get("source_sha16") == sha:
+                traffic, traffic_note = rec.get("dram_bytes_per_launch"), f"ncu --set full capture {rec.get('capture')} of this kernel source"
         except Exception:
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"icosphere f={f} ({nel_global} triangles global, {nel_local} per GPU), radial perturbation 1%, seed 12345; "
-                               "step = Area.gradient + VolumeEnclosed.gradient (2 element-evals per triangle)",
-                   "inputs": "larger than L2 (vertex matrix 120 MB + ring tables 101 MB + gradient 120 MB per functional)",
+        "config": {"workload": workload_string(f, world), "inputs": INPUTS,
                    "partition": "contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) and summed in rank order" if world > 1 else "single GPU",
                    "gradient_path": "persistent patch kernel: bulk-async (TMA) staging of vertex runs into a 3-stage shared-memory ring, one consumer thread per owned vertex walks its ring (owner computes, no atomics)",
                    "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol, "shared_row_exchange": ms_exch if world > 1 else 0.0}},
@@ -391,8 +492,15 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": f"of {how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "of fallback",
                      "algorithmic_bytes_per_element": BYTES_PER_ELEM_GRADIENT, "elements_per_launch": nel_local,
-                     "avg_launch_ms": ms_dom, "traffic": traffic},
+                     "avg_launch_ms": ms_dom, "traffic": traffic, "traffic_source": traffic_note},
     }
+    if parity is not None:
+        line["parity"] = parity
+    if world == 1 and not args.no_configs:
+        # the other single-GPU configs of BASELINE.json, measured in this same run (scripts/bench_configs.py)
+        from scripts.bench_configs import run_all
+        mesh = None
+        line["configs"] = run_all(mb, torch, peak, log=log)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(vert, conn)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -409,6 +517,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--freq", type=int, default=707, help="icosphere frequency per GPU (707 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the gradients before timing")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3/4/5 (N=1 only)")
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")

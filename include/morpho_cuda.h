@@ -250,6 +250,8 @@ long mcu_launch_count(void);                /* kernels launched by this library 
 int mcu_device_malloc(void **ptr, size_t bytes);
 int mcu_device_free(void *ptr);
 int mcu_flush_l2(void);                     /* overwrite a > L2-sized scratch buffer */
+/* FP64 peak of the device from a DFMA micro-benchmark (2 flop per DFMA): the roofline denominator of the pairwise kernel */
+int mcu_debug_dfma_peak(double *tflops);
 
 /* ---- introspection of the patch planner (pure host code, no CUDA call): used by the CPU tests
  *      of the host logic.  counts = {patches, runs, table words, ints per header, max slots, max table

@@ -102,6 +102,7 @@ def lib():
         "mcu_device_malloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "mcu_device_free": (C.c_int, [vp]),
         "mcu_flush_l2": (C.c_int, []),
+        "mcu_debug_dfma_peak": (C.c_int, [dp]),
         "mcu_halo_create": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]),
         "mcu_halo_export": (C.c_int, [vp, vp]),
         "mcu_halo_connect": (C.c_int, [vp, vp]),
