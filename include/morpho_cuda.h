@@ -78,6 +78,7 @@ enum {
 typedef struct mcu_mesh mcu_mesh;           /* device mirror of objectmesh      (mesh.h:25-31)      */
 typedef struct mcu_field mcu_field;         /* device mirror of objectfield     (field.h:25-41)     */
 typedef struct mcu_selection mcu_selection; /* device mirror of objectselection (selection.h:22-31) */
+typedef struct mcu_matrix mcu_matrix;       /* device-resident objectmatrix         (matrix.h:65-73)    */
 
 /* Call descriptor: the part of functional_mapinfo (functional.h:226-241) plus the
  * per-class reference structs (curvatureref functional.c:2935-2939, fieldref 3436-3439,
@@ -154,6 +155,39 @@ int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, in
 int mcu_mesh_status(mcu_mesh *m);
 /* number of doubles `mode` produces for this functional on this mesh */
 long mcu_result_size(mcu_mesh *m, const mcu_functional *f, int mode);
+
+/* ---- Device-resident Matrix objects and the vector operations of the optimisers.
+ *      optimize.morpho's line search is `vsave = x.clone(); x.acc(-s, force); totals; mesh.setvertexmatrix(vsave)` and
+ *      its iterations combine gradients with inner / norm / acc / scalar multiples / column writes
+ *      (optimize.morpho:229-303, 461-486, 686-693); the reference runs them as cblas_daxpy / ddot / dnrm2 / dscal on host
+ *      arrays.  With these entry points a matrix lives on the device for its whole life: the extension
+ *      keeps a lazily synchronised host copy only for readers it does not accelerate.  Layout: column-major
+ *      nrows x ncols doubles, as objectmatrix.elements.  Reductions are deterministic (fixed chunks, compensated sums).
+ *        mcu_matrix_axpby   out <- sa a + sb b (b NULL: sa a)   matrix_axpy / Matrix +,- / matrix_scale  matrix.c:495-500, 526-529, 1098-1160
+ *        mcu_matrix_xpa     out <- a sgn + beta                 matrix_addscalar                          matrix.c:557-565
+ *        mcu_matrix_copy    dst <- src                          matrix_copy / matrix_clone                matrix.c:310-320, 503-509
+ *        mcu_matrix_inner / norm / sum                          matrix_inner / matrix_norm / matrix_sum   matrix.c:586-604, 621-626
+ *        mcu_matrix_set_column / get_column / zero_columns      matrix_setcolumn / getcolumn; Optimizer.fixgrad  matrix.c:447-463
+ *      mcu_mesh_bind_vertices makes a mesh read its vertices from such a matrix (Mesh.setvertexmatrix, mesh.c:1145-1160)
+ *      without a copy; mcu_eval_matrix evaluates a gradient / integrand straight into one. ---- */
+mcu_matrix *mcu_matrix_create(int nrows, int ncols);
+int mcu_matrix_destroy(mcu_matrix *m);
+int mcu_matrix_dims(const mcu_matrix *m, int *nrows, int *ncols);
+double *mcu_matrix_device(mcu_matrix *m);
+int mcu_matrix_upload(mcu_matrix *m, const double *host);
+int mcu_matrix_download(mcu_matrix *m, double *host);
+int mcu_matrix_copy(mcu_matrix *dst, const mcu_matrix *src);
+int mcu_matrix_zero(mcu_matrix *m);
+int mcu_matrix_axpby(mcu_matrix *out, const mcu_matrix *a, double sa, const mcu_matrix *b, double sb);
+int mcu_matrix_xpa(mcu_matrix *out, const mcu_matrix *a, double sgn, double beta);
+int mcu_matrix_inner(mcu_matrix *a, const mcu_matrix *b, double *host_out);
+int mcu_matrix_norm(mcu_matrix *a, double *host_out);
+int mcu_matrix_sum(mcu_matrix *a, double *host_out);
+int mcu_matrix_set_column(mcu_matrix *m, int col, const double *host_col);
+int mcu_matrix_get_column(mcu_matrix *m, int col, double *host_col);
+int mcu_matrix_zero_columns(mcu_matrix *m, int n, const int *host_cols);
+int mcu_mesh_bind_vertices(mcu_mesh *m, mcu_matrix *vert);
+int mcu_eval_matrix(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, mcu_matrix *out);
 
 /* ---- Line / area integrals of an integrand over the elements: integrate_integrate (integrate.c:769-800), the default
  *      element integrator behind LineIntegral / AreaIntegral (functional.c:5176-5245, 5354-5428): adaptive Gauss-Kronrod

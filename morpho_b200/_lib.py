@@ -91,6 +91,24 @@ def lib():
         "mcu_eval_device": (C.c_int, [vp, C.POINTER(McuFunctional), vp, C.c_int, vp]),
         "mcu_result_size": (C.c_long, [vp, C.POINTER(McuFunctional), C.c_int]),
         "mcu_mesh_status": (C.c_int, [vp]),
+        "mcu_matrix_create": (vp, [C.c_int, C.c_int]),
+        "mcu_matrix_destroy": (C.c_int, [vp]),
+        "mcu_matrix_dims": (C.c_int, [vp, ip, ip]),
+        "mcu_matrix_device": (vp, [vp]),
+        "mcu_matrix_upload": (C.c_int, [vp, vp]),
+        "mcu_matrix_download": (C.c_int, [vp, vp]),
+        "mcu_matrix_copy": (C.c_int, [vp, vp]),
+        "mcu_matrix_zero": (C.c_int, [vp]),
+        "mcu_matrix_axpby": (C.c_int, [vp, vp, C.c_double, vp, C.c_double]),
+        "mcu_matrix_xpa": (C.c_int, [vp, vp, C.c_double, C.c_double]),
+        "mcu_matrix_inner": (C.c_int, [vp, vp, dp]),
+        "mcu_matrix_norm": (C.c_int, [vp, dp]),
+        "mcu_matrix_sum": (C.c_int, [vp, dp]),
+        "mcu_matrix_set_column": (C.c_int, [vp, C.c_int, vp]),
+        "mcu_matrix_get_column": (C.c_int, [vp, C.c_int, vp]),
+        "mcu_matrix_zero_columns": (C.c_int, [vp, C.c_int, vp]),
+        "mcu_mesh_bind_vertices": (C.c_int, [vp, vp]),
+        "mcu_eval_matrix": (C.c_int, [vp, C.POINTER(McuFunctional), vp, C.c_int, vp]),
         "mcu_pairwise_program": (C.c_int, [C.c_int, vp, C.c_int, vp]),
         "mcu_pairwise": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),
         "mcu_pairwise_device": (C.c_int, [C.c_int, C.c_int, vp, C.c_int, vp, C.c_double, C.c_int, vp]),

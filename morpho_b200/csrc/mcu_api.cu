@@ -39,6 +39,7 @@ void mcu_set_error(const char *fmt, ...) {
 }
 
 cudaStream_t mcu_stream() { return g_stream; }
+int mcu_init_if_needed() { return g_inited ? MCU_OK : mcu_init(g_device < 0 ? 0 : g_device); }
 long mcu_opt(const char *key, long dflt) {
     auto it = g_opts.find(key);
     return it == g_opts.end() ? dflt : it->second;
@@ -169,6 +170,7 @@ mcu_mesh *mcu_mesh_create(int dim, int nv) {
         return nullptr;
     }
     cudaMemsetAsync(m->d_flags, 0, 64, g_stream);
+    m->d_vert_own = m->d_vert;
     return m;
 }
 
@@ -185,7 +187,7 @@ int mcu_mesh_destroy(mcu_mesh *m) {
     if (!m) return MCU_OK;
     cudaStreamSynchronize(g_stream);
     for (int g = 0; g < 4; g++) conn_free(m, m->conn[g]);
-    cudaFree(m->d_vert); cudaFree(m->d_partials); cudaFree(m->d_scalar); cudaFree(m->d_flags);
+    cudaFree(m->d_vert_own); cudaFree(m->d_partials); cudaFree(m->d_scalar); cudaFree(m->d_flags);
     if (m->d_result) cudaFree(m->d_result);
     delete m;
     return MCU_OK;
@@ -193,7 +195,22 @@ int mcu_mesh_destroy(mcu_mesh *m) {
 
 int mcu_mesh_set_vertices(mcu_mesh *m, const double *host) {
     if (!m || !host) { mcu_set_error("null argument"); return MCU_ERR_ARGS; }
+    m->d_vert = m->d_vert_own; m->bound = nullptr;       // an upload always lands in the mesh's own buffer
     CK(cudaMemcpyAsync(m->d_vert, host, sizeof(double) * (size_t) m->nv * m->dim, cudaMemcpyHostToDevice, g_stream));
+    m->vert_version++;
+    return MCU_OK;
+}
+
+/* Mesh.setvertexmatrix with a device-resident Matrix (mesh.c:1145-1160 swaps the pointer mesh->vert; so does this):
+ * the kernels read the vertices straight from `vert`, no copy.  NULL returns to the mesh's own buffer, whose contents
+ * are then stale until the next mcu_mesh_set_vertices.  The matrix must outlive the binding. */
+int mcu_mesh_bind_vertices(mcu_mesh *m, mcu_matrix *vert) {
+    if (!m) { mcu_set_error("null argument"); return MCU_ERR_ARGS; }
+    if (!vert) { m->d_vert = m->d_vert_own; m->bound = nullptr; return MCU_OK; }
+    int nr = 0, nc = 0;
+    mcu_matrix_dims(vert, &nr, &nc);
+    if (nr != m->dim || nc != m->nv) { mcu_set_error("Vertex matrix dimensions inconsistent with mesh."); return MCU_ERR_ARGS; }
+    m->d_vert = mcu_matrix_device(vert); m->bound = vert;
     m->vert_version++;
     return MCU_OK;
 }
@@ -597,6 +614,17 @@ int mcu_eval_device(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, in
     NEED_INIT();
     if (!m || !f || !dev_out) { mcu_set_error("null argument"); return MCU_ERR_ARGS; }
     return eval_impl(m, f, sel, mode, dev_out);
+}
+
+/* the gradient / integrand straight into a device-resident Matrix (the object the builtin returns stays on the device) */
+int mcu_eval_matrix(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, mcu_matrix *out) {
+    NEED_INIT();
+    if (!m || !f || !out) { mcu_set_error("null argument"); return MCU_ERR_ARGS; }
+    long n = mcu_result_size(m, f, mode);
+    int nr = 0, nc = 0;
+    mcu_matrix_dims(out, &nr, &nc);
+    if (n < 0 || (long) nr * nc != n) { mcu_set_error("result matrix has the wrong size"); return MCU_ERR_ARGS; }
+    return eval_impl(m, f, sel, mode, mcu_matrix_device(out));
 }
 
 int mcu_eval(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *host_out) {

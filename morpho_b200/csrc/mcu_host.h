@@ -21,7 +21,9 @@ struct McuConn {
 
 struct mcu_mesh {
     int dim = 0, nv = 0;
-    double *d_vert = nullptr;
+    double *d_vert = nullptr;        // the vertex store the kernels read: the mesh's own buffer or a bound mcu_matrix
+    double *d_vert_own = nullptr;    // the mesh's own buffer
+    struct mcu_matrix *bound = nullptr;
     McuConn conn[4];
     long vert_version = 0, conn_version = 0;
     CompSum *d_partials = nullptr;
@@ -51,6 +53,7 @@ struct mcu_selection {
 
 void mcu_set_error(const char *fmt, ...);
 cudaStream_t mcu_stream();
+int mcu_init_if_needed();
 long mcu_opt(const char *key, long dflt);
 void mcu_host_transpose(int nv, int n, int nvper, const int *rix, const int *eids, std::vector<int> &tptr, std::vector<int> &tidx);
 

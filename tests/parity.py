@@ -33,7 +33,18 @@ EPS_FLOOR = 1e-2       # per-vertex measure: floor as a fraction of the vertex's
 
 # 10x the worst error observed on the B200 (tests/test_parity_gpu.py::test_cuda_matches_reference_golden over all
 # golden cases; observed values: profiles/r2_parity_errors.json).  Keys: (functional, method).
-FD_TOL = {}
+FD_TOL = {
+    ("AreaEnclosed", "gradient"): 2.6e-11,            # observed 2.6e-12
+    ("GradSq", "fieldgradient"): 5.0e-10,             # observed 5.0e-11
+    ("GradSq", "gradient"): 1.9e-10,                  # observed 1.9e-11
+    ("LineCurvatureSq", "gradient"): 8.8e-11,         # observed 8.7e-12
+    ("Nematic", "fieldgradient"): 8.5e-11,            # observed 8.5e-12
+    ("Nematic", "gradient"): 1.8e-10,                 # observed 1.8e-11
+    ("NematicElectric", "fieldgradient"): 5.2e-11,    # observed 5.2e-12
+    ("NematicElectric", "gradient"): 1.7e-11,         # observed 1.7e-12
+    ("NormSq", "fieldgradient"): 3.4e-10,             # observed 3.3e-11
+    ("NormSq", "gradient"): 1e-12,                    # observed 0 (identically zero in the reference too)
+}
 
 
 _recorded = {}

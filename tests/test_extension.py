@@ -136,8 +136,8 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,tol", [("functionals_basic.morpho", 1e-12), ("catenoid_cg.morpho", 1e-9),
-                                      ("volume_constraint.morpho", 1e-9), ("field_functionals.morpho", 1e-9)])
+@pytest.mark.parametrize("name,tol", [("functionals_basic.morpho", 1e-12), ("catenoid_cg.morpho", 1e-12),
+                                      ("volume_constraint.morpho", 1e-11), ("field_functionals.morpho", 1e-9)])
 def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
     src = script(name)
     ref, _ = run(src, tmp_path, "stock.morpho")
