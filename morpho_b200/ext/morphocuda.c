@@ -41,11 +41,14 @@
 #include "field.h"
 #include "functional.h"
 
+#include <math.h>
+
 #include "morpho_cuda.h"
 #include "mc_translate.h"
+#include "mc_resident.h"
 
 #define MC_MAXMIRRORS 64
-#define MC_MAXWRAPS 48
+#define MC_MAXWRAPS 1024
 
 typedef struct {
     objectmesh *mesh;
@@ -54,6 +57,7 @@ typedef struct {
     double *elements;        /* vert->elements when last mirrored */
     int nv, dim;
     bool vert_dirty;
+    mcu_matrix *bound;       /* the device-resident Matrix (mc_resident.h) the mesh reads its vertices from, or NULL */
     struct { objectsparse *s; int *rix; int nel; bool ok; } conn[4];
 } mc_mirror;
 
@@ -85,6 +89,12 @@ static void mirror_mark_matrix(objectmatrix *a) {
         if (mirrors[i].vert == a || mirrors[i].elements == a->elements) mirrors[i].vert_dirty = true;
 }
 
+/* a device-resident Matrix is going away (mc_resident.h shadow_drop): mirrors reading from it return to their own buffer */
+static void mirror_unbind_matrix(mcu_matrix *d) {
+    for (int i = 0; i < nmirrors; i++)
+        if (mirrors[i].bound == d) { mcu_mesh_bind_vertices(mirrors[i].m, NULL); mirrors[i].bound = NULL; mirrors[i].vert_dirty = true; }
+}
+
 static void mirror_invalidate_connectivity(objectmesh *mesh) {
     for (int i = 0; i < nmirrors; i++)
         if (!mesh || mirrors[i].mesh == mesh) for (int g = 0; g < 4; g++) mirrors[i].conn[g].ok = false;
@@ -109,10 +119,27 @@ static mc_mirror *mirror_get(objectmesh *mesh, grade g) {
     if (mr->vert != mesh->vert || mr->elements != mesh->vert->elements) {   /* Mesh.setvertexmatrix swapped the matrix */
         mr->vert = mesh->vert; mr->elements = mesh->vert->elements; mr->vert_dirty = true;
     }
-    if (mr->vert_dirty || mc_paranoid) {
-        if (mcu_mesh_set_vertices(mr->m, mesh->vert->elements) != MCU_OK) return NULL;
+    /* a vertex matrix large enough to live on the device (mc_resident.h) is READ IN PLACE: the mirror binds to the
+     * Matrix's shadow, so `x.acc(-s, force)` of a line search is seen without any copy and Mesh.setvertexmatrix is a
+     * pointer swap here as it is in the reference (mesh.c:1145-1160) */
+    mc_shadow *vs = shadow_find(mesh->vert);
+    if (!vs && shadow_eligible(mesh->vert) && !mc_paranoid) vs = shadow_create(mesh->vert, true, false);
+    if (vs && !mc_paranoid) {
+        if (!vs->dev_valid) mc_stat_vert_uploads++;
+        if (!shadow_to_device(vs)) return NULL;
+        if (mr->bound != vs->d) {
+            if (mcu_mesh_bind_vertices(mr->m, vs->d) != MCU_OK) return NULL;
+            mr->bound = vs->d;
+        }
         mr->vert_dirty = false;
-        mc_stat_vert_uploads++;
+    } else {
+        if (vs && !shadow_to_host(vs)) return NULL;
+        if (mr->bound) { mcu_mesh_bind_vertices(mr->m, NULL); mr->bound = NULL; mr->vert_dirty = true; }
+        if (mr->vert_dirty || mc_paranoid) {
+            if (mcu_mesh_set_vertices(mr->m, mesh->vert->elements) != MCU_OK) return NULL;
+            mr->vert_dirty = false;
+            mc_stat_vert_uploads++;
+        }
     }
     if (g > 0) {
         objectsparse *s = mesh_getconnectivityelement(mesh, 0, g);
@@ -206,6 +233,27 @@ static bool mesh_has_symmetries(objectmesh *mesh, grade g) {
     return mesh_getconnectivityelement(mesh, 0, 0) || (g > 0 && mesh_getconnectivityelement(mesh, g, g));
 }
 
+/* A Matrix-valued result (gradient / integrand).  Large results stay on the device: the objectmatrix the builtin
+ * returns is shadowed by the mcu_matrix the kernels wrote (mc_resident.h) and its host array is filled only if something
+ * that is not accelerated reads it.  Small ones are copied to the host at once, as the reference would have them. */
+static int eval_matrix_result(mc_mirror *mr, const mcu_functional *f, mcu_selection *sel, int mode, MatrixIdx_t nr, MatrixIdx_t nc, objectmatrix **out) {
+    objectmatrix *new = matrix_new(nr, nc, false);
+    *out = new;
+    if (!new) return -1;
+    if ((long) nr * nc == 0) return MCU_OK;
+    if (shadow_eligible(new) && !mc_paranoid) {
+        mc_shadow *s = shadow_create(new, false, true);
+        if (s) {
+            int rc = mcu_eval_matrix(mr->m, f, sel, mode, s->d);
+            if (rc == MCU_OK) rc = mcu_mesh_status(mr->m);          /* degenerate element / VolEnclZero raised by the kernels */
+            if (rc != MCU_OK) shadow_drop(shadow_find(new));
+            else mc_stat_devops++;
+            return rc;
+        }
+    }
+    return mcu_eval(mr->m, f, sel, mode, new->elements);
+}
+
 /* One evaluation; returns true when handled (out/err set), false → call the reference builtin */
 static bool mc_eval(vm *v, int nargs, value *args, int functional, grade g, int mode, value *out) {
     functional_mapinfo info;
@@ -240,15 +288,13 @@ static bool mc_eval(vm *v, int nargs, value *args, int functional, grade g, int 
             break;
         case MCU_INTEGRAND: {
             long n = mcu_result_size(mr->m, &f, MCU_INTEGRAND);
-            new = matrix_new(1, (MatrixIdx_t) n, false);
-            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
-            if (n > 0) rc = mcu_eval(mr->m, &f, sel, MCU_INTEGRAND, new->elements);
+            rc = eval_matrix_result(mr, &f, sel, MCU_INTEGRAND, 1, (MatrixIdx_t) n, &new);
+            if (rc == -1) morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED);
             break;
         }
         case MCU_GRADIENT:
-            new = matrix_new(mr->dim, mr->nv, false);
-            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
-            rc = mcu_eval(mr->m, &f, sel, MCU_GRADIENT, new->elements);
+            rc = eval_matrix_result(mr, &f, sel, MCU_GRADIENT, mr->dim, mr->nv, &new);
+            if (rc == -1) morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED);
             break;
         default:
             rc = MCU_ERR_UNSUPPORTED;
@@ -357,14 +403,12 @@ static bool mc_eval_props(vm *v, int nargs, value *args, int functional, int mod
     else switch (mode) {
         case MCU_TOTAL: rc = mcu_eval(mr->m, &f, sel, MCU_TOTAL, &total); break;
         case MCU_INTEGRAND:
-            new = matrix_new(1, (MatrixIdx_t) n, false);
-            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
-            if (n > 0) rc = mcu_eval(mr->m, &f, sel, MCU_INTEGRAND, new->elements);
+            rc = eval_matrix_result(mr, &f, sel, MCU_INTEGRAND, 1, (MatrixIdx_t) n, &new);
+            if (rc == -1) morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED);
             break;
         case MCU_GRADIENT:
-            new = matrix_new(mr->dim, mr->nv, false);
-            if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; break; }
-            rc = mcu_eval(mr->m, &f, sel, MCU_GRADIENT, new->elements);
+            rc = eval_matrix_result(mr, &f, sel, MCU_GRADIENT, mr->dim, mr->nv, &new);
+            if (rc == -1) morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED);
             break;
         case MCU_FIELDGRADIENT:
             newf = object_newfield(info.mesh, wrtfield->prototype, wrtfield->fnspc, wrtfield->dof);   /* functional.c:1449 */
@@ -610,36 +654,62 @@ MC_FUNCTIONAL(Volume, MCU_F_VOLUME, MESH_GRADE_VOLUME)
 MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, total, MCU_TOTAL)
 MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, integrand, MCU_INTEGRAND)
 
-/* ------------------------------------------------------------------ write hooks */
+/* ------------------------------------------------------------------ hooks on the VM's builtins */
 
-typedef enum { WRAP_MATRIX_SELF, WRAP_MESH_VERTS, WRAP_MESH_CONN, WRAP_CONN_ALL } mc_wrapkind;
-static struct { builtinfunction orig; mc_wrapkind kind; } wraps[MC_MAXWRAPS];
+/* Every builtin the extension does not replace outright passes through a numbered trampoline:
+ *   accel   an accelerated Matrix method (mc_resident.h) is tried first;
+ *   flush   before the reference builtin runs, Matrix arguments (and the vertex matrix of Mesh arguments) whose
+ *           newest copy is on the device are brought to the host;
+ *   post    what the builtin wrote: the receiver Matrix (its device copy and the mirrors reading it are stale), a
+ *           mesh's vertices, connectivity. */
+typedef enum { WRAP_NONE, WRAP_MATRIX_SELF, WRAP_MATRIX_RESHAPE, WRAP_MESH_VERTS, WRAP_MESH_CONN, WRAP_CONN_ALL } mc_wrapkind;
+static struct { builtinfunction orig; mc_wrapkind kind; mc_accel accel; bool flush; } wraps[MC_MAXWRAPS];
 static int nwraps = 0;
 
 static value wrap_call(int slot, vm *v, int nargs, value *args) {
-    value self = MORPHO_SELF(args);
+    value self = MORPHO_SELF(args), r;
+    if (wraps[slot].accel != ACC_NONE && accel_call(wraps[slot].accel, v, nargs, args, &r)) return r;
+    if (wraps[slot].flush) shadow_flush_args(nargs, args);
     /* resolve the target BEFORE the call (the method may free or replace things), mark AFTER it */
-    objectmatrix *mat = (wraps[slot].kind == WRAP_MATRIX_SELF && MORPHO_ISMATRIX(self)) ? MORPHO_GETMATRIX(self) : NULL;
-    objectmesh *mesh = ((wraps[slot].kind == WRAP_MESH_VERTS || wraps[slot].kind == WRAP_MESH_CONN) && MORPHO_ISMESH(self)) ? MORPHO_GETMESH(self) : NULL;
-    value r = wraps[slot].orig(v, nargs, args);
-    switch (wraps[slot].kind) {
-        case WRAP_MATRIX_SELF: if (mat) mirror_mark_matrix(mat); break;
-        case WRAP_MESH_VERTS: { mc_mirror *mr = mesh ? mirror_find(mesh) : NULL; if (mr) mr->vert_dirty = true; break; }
+    mc_wrapkind kind = wraps[slot].kind;
+    objectmatrix *mat = ((kind == WRAP_MATRIX_SELF || kind == WRAP_MATRIX_RESHAPE) && MORPHO_ISMATRIX(self)) ? MORPHO_GETMATRIX(self) : NULL;
+    objectmesh *mesh = ((kind == WRAP_MESH_VERTS || kind == WRAP_MESH_CONN) && MORPHO_ISMESH(self)) ? MORPHO_GETMESH(self) : NULL;
+    r = wraps[slot].orig(v, nargs, args);
+    switch (kind) {
+        case WRAP_NONE: break;
+        case WRAP_MATRIX_SELF: case WRAP_MATRIX_RESHAPE:
+            if (mat) {
+                mirror_mark_matrix(mat);
+                mc_shadow *sh = shadow_find(mat);                 /* written on the host (flushed above): device copy stale */
+                if (sh && kind == WRAP_MATRIX_RESHAPE) shadow_drop(sh);
+                else if (sh) sh->dev_valid = false;
+            }
+            break;
+        case WRAP_MESH_VERTS: {
+            mc_mirror *mr = mesh ? mirror_find(mesh) : NULL;
+            if (mr) mr->vert_dirty = true;
+            if (mesh && mesh->vert && wraps[slot].flush) { mc_shadow *sh = shadow_find(mesh->vert); if (sh) sh->dev_valid = false; }
+            break;
+        }
         case WRAP_MESH_CONN: mirror_invalidate_connectivity(mesh); break;
         case WRAP_CONN_ALL: mirror_invalidate_connectivity(NULL); break;
     }
     return r;
 }
 /* C has no closures: a pool of numbered trampolines, one per wrapped builtin */
-#define TR(n) static value tr_##n(vm *v, int nargs, value *args) { return wrap_call(n, v, nargs, args); }
-TR(0) TR(1) TR(2) TR(3) TR(4) TR(5) TR(6) TR(7) TR(8) TR(9) TR(10) TR(11) TR(12) TR(13) TR(14) TR(15)
-TR(16) TR(17) TR(18) TR(19) TR(20) TR(21) TR(22) TR(23) TR(24) TR(25) TR(26) TR(27) TR(28) TR(29) TR(30) TR(31)
-TR(32) TR(33) TR(34) TR(35) TR(36) TR(37) TR(38) TR(39) TR(40) TR(41) TR(42) TR(43) TR(44) TR(45) TR(46) TR(47)
-#define TRN(n) tr_##n
-static builtinfunction trampolines[MC_MAXWRAPS] = {
-    TRN(0), TRN(1), TRN(2), TRN(3), TRN(4), TRN(5), TRN(6), TRN(7), TRN(8), TRN(9), TRN(10), TRN(11), TRN(12), TRN(13), TRN(14), TRN(15),
-    TRN(16), TRN(17), TRN(18), TRN(19), TRN(20), TRN(21), TRN(22), TRN(23), TRN(24), TRN(25), TRN(26), TRN(27), TRN(28), TRN(29), TRN(30), TRN(31),
-    TRN(32), TRN(33), TRN(34), TRN(35), TRN(36), TRN(37), TRN(38), TRN(39), TRN(40), TRN(41), TRN(42), TRN(43), TRN(44), TRN(45), TRN(46), TRN(47)};
+#define TR(n) static value tr_##n(vm *v, int nargs, value *args) { return wrap_call(0x##n, v, nargs, args); }
+#define TR16(p) TR(p##0) TR(p##1) TR(p##2) TR(p##3) TR(p##4) TR(p##5) TR(p##6) TR(p##7) TR(p##8) TR(p##9) TR(p##a) TR(p##b) TR(p##c) TR(p##d) TR(p##e) TR(p##f)
+#define TR256(p) TR16(p##0) TR16(p##1) TR16(p##2) TR16(p##3) TR16(p##4) TR16(p##5) TR16(p##6) TR16(p##7) TR16(p##8) TR16(p##9) TR16(p##a) TR16(p##b) TR16(p##c) TR16(p##d) TR16(p##e) TR16(p##f)
+TR256(0) TR256(1) TR256(2) TR256(3)
+#define TRN(n) tr_##n,
+#define TRN16(p) TRN(p##0) TRN(p##1) TRN(p##2) TRN(p##3) TRN(p##4) TRN(p##5) TRN(p##6) TRN(p##7) TRN(p##8) TRN(p##9) TRN(p##a) TRN(p##b) TRN(p##c) TRN(p##d) TRN(p##e) TRN(p##f)
+#define TRN256(p) TRN16(p##0) TRN16(p##1) TRN16(p##2) TRN16(p##3) TRN16(p##4) TRN16(p##5) TRN16(p##6) TRN16(p##7) TRN16(p##8) TRN16(p##9) TRN16(p##a) TRN16(p##b) TRN16(p##c) TRN16(p##d) TRN16(p##e) TRN16(p##f)
+static builtinfunction trampolines[MC_MAXWRAPS] = { TRN256(0) TRN256(1) TRN256(2) TRN256(3) };
+
+static int trampoline_index(builtinfunction fn) {
+    for (int k = 0; k < MC_MAXWRAPS; k++) if (fn == trampolines[k]) return k;
+    return -1;
+}
 
 /* every builtin implementation behind class.method (a plain builtin or the members of a metafunction) */
 static int method_impls(const char *cls, const char *method, objectbuiltinfunction **out, int cap) {
@@ -659,17 +729,74 @@ static int method_impls(const char *cls, const char *method, objectbuiltinfuncti
     return n;
 }
 
-static int hook_writers(const char *cls, const char *method, mc_wrapkind kind) {
+/* wrap one builtin implementation (or refine the wrap it already has) */
+static int hook_impl(objectbuiltinfunction *impl, mc_wrapkind kind, mc_accel accel, bool flush) {
+    int k = trampoline_index(impl->function);
+    if (k >= 0) {                                             /* wrapped already (generic pass, or registered under two names) */
+        if (kind != WRAP_NONE) wraps[k].kind = kind;
+        if (accel != ACC_NONE) wraps[k].accel = accel;
+        wraps[k].flush = flush;
+        return 0;
+    }
+    if (nwraps == MC_MAXWRAPS) { fprintf(stderr, "[morphocuda] out of trampolines\n"); return 0; }
+    wraps[nwraps].orig = impl->function; wraps[nwraps].kind = kind; wraps[nwraps].accel = accel; wraps[nwraps].flush = flush;
+    impl->function = trampolines[nwraps++];
+    return 1;
+}
+
+static int hook_method(const char *cls, const char *method, mc_wrapkind kind, mc_accel accel, bool flush) {
     objectbuiltinfunction *impl[16];
     int n = method_impls(cls, method, impl, 16), done = 0;
-    for (int i = 0; i < n; i++) {
-        bool ours = false;
-        for (int k = 0; k < MC_MAXWRAPS; k++) if (impl[i]->function == trampolines[k]) ours = true;
-        if (ours) continue;                                   /* the same builtin registered under two names */
-        if (nwraps == MC_MAXWRAPS) { fprintf(stderr, "[morphocuda] out of trampolines for %s.%s\n", cls, method); break; }
-        wraps[nwraps].orig = impl[i]->function; wraps[nwraps].kind = kind;
-        impl[i]->function = trampolines[nwraps++];
-        done++;
+    for (int i = 0; i < n; i++) done += hook_impl(impl[i], kind, accel, flush);
+    return done;
+}
+#define hook_writers(cls, method, kind) hook_method(cls, method, kind, ACC_NONE, true)
+
+/* The generic pass: every method of every builtin class except plain containers and scalars, and every builtin
+ * function, flushes its Matrix / Mesh arguments first.  (Lists, tuples, dictionaries, strings and ranges never read
+ * the elements of a Matrix they hold; printing goes through Matrix.print, which is a method and is wrapped.) */
+static bool class_is_plain(objectclass *klass) {
+    static const char *skip[] = {"Object", "List", "Tuple", "Dictionary", "String", "Range", "Int", "Float", "Bool", "Nil", "Function",
+                                 "Closure", "Invocation", "Error", "Class", "Metafunction", "BuiltinFunction", "Upvalue", "Instance",
+                                 "DictionaryEntry", "Complex", "File", "Folder", "System", "JSON", NULL};
+    if (!MORPHO_ISSTRING(klass->name)) return false;
+    for (int i = 0; skip[i]; i++) if (strcmp(MORPHO_GETCSTRING(klass->name), skip[i]) == 0) return true;
+    return false;
+}
+
+static int hook_value(value m) {
+    int done = 0;
+    if (MORPHO_ISBUILTINFUNCTION(m)) done += hook_impl(MORPHO_GETBUILTINFUNCTION(m), WRAP_NONE, ACC_NONE, true);
+    else if (MORPHO_ISMETAFUNCTION(m)) {
+        objectmetafunction *mf = MORPHO_GETMETAFUNCTION(m);
+        for (unsigned int i = 0; i < mf->fns.count; i++)
+            if (MORPHO_ISBUILTINFUNCTION(mf->fns.data[i])) done += hook_impl(MORPHO_GETBUILTINFUNCTION(mf->fns.data[i]), WRAP_NONE, ACC_NONE, true);
+    }
+    return done;
+}
+
+static value mc_stats(vm *v, int nargs, value *args);
+static value mc_translate_fn(vm *v, int nargs, value *args);
+/* while an extension initialises, builtin_getclasstable() / builtin_getfunctiontable() are the extension's own (empty)
+ * tables (extensions.c:140-156); the VM's are these globals of builtin.c:27-30 */
+extern dictionary builtin_functiontable, builtin_classtable;
+
+static int hook_everything(void) {
+    int done = 0;
+    dictionary *classes = &builtin_classtable, *fns = &builtin_functiontable;
+    for (unsigned int i = 0; i < classes->capacity; i++) {
+        if (MORPHO_ISNIL(classes->contents[i].key) || !MORPHO_ISCLASS(classes->contents[i].val)) continue;
+        objectclass *klass = MORPHO_GETCLASS(classes->contents[i].val);
+        if (class_is_plain(klass)) continue;
+        for (unsigned int k = 0; k < klass->methods.capacity; k++)
+            if (!MORPHO_ISNIL(klass->methods.contents[k].key)) done += hook_value(klass->methods.contents[k].val);
+    }
+    for (unsigned int i = 0; i < fns->capacity; i++) {
+        if (MORPHO_ISNIL(fns->contents[i].key)) continue;
+        value fv = fns->contents[i].val;
+        /* our own helpers are registered in this table too */
+        if (MORPHO_ISBUILTINFUNCTION(fv) && (MORPHO_GETBUILTINFUNCTION(fv)->function == mc_stats || MORPHO_GETBUILTINFUNCTION(fv)->function == mc_translate_fn)) continue;
+        done += hook_value(fv);
     }
     return done;
 }
@@ -692,15 +819,25 @@ static void mc_meshfree(object *obj) {
     if (orig_meshfree) orig_meshfree(obj);
 }
 
+/* Matrix objects that die take their device shadow with them (objectmatrixdefn.freefn is NULL in the reference) */
+static objectfreefn orig_matrixfree = NULL;
+static void mc_matrixfree(object *obj) {
+    if (nshadows > 0) { mc_shadow *s = shadow_find((objectmatrix *) obj); if (s) shadow_drop(s); }
+    if (orig_matrixfree) orig_matrixfree(obj);
+}
+
 /* ------------------------------------------------------------------ script-visible helpers */
 
 /* cudastats() → List [evaluations on the GPU, vertex uploads, connectivity uploads, calls left to the reference, field uploads,
- * integrand closures translated] */
+ * integrand closures translated, Matrix operations run on device-resident matrices, matrices copied back to the host for a
+ * reader that is not accelerated, bytes host→device and device→host moved for resident matrices] */
 static value mc_stats(vm *v, int nargs, value *args) {
-    value vals[6] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
-                     MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks),
-                     MORPHO_INTEGER((int) mc_stat_field_uploads), MORPHO_INTEGER((int) mc_stat_translated)};
-    objectlist *l = object_newlist(6, vals);
+    value vals[10] = {MORPHO_INTEGER((int) mc_stat_evals), MORPHO_INTEGER((int) mc_stat_vert_uploads),
+                      MORPHO_INTEGER((int) mc_stat_conn_uploads), MORPHO_INTEGER((int) mc_stat_fallbacks),
+                      MORPHO_INTEGER((int) mc_stat_field_uploads), MORPHO_INTEGER((int) mc_stat_translated),
+                      MORPHO_INTEGER((int) mc_stat_devops), MORPHO_INTEGER((int) mc_stat_flushes),
+                      MORPHO_FLOAT(mc_stat_h2d_bytes), MORPHO_FLOAT(mc_stat_d2h_bytes)};
+    objectlist *l = object_newlist(10, vals);
     if (!l) return MORPHO_NIL;
     return morpho_wrapandbind(v, (object *) l);
 }
@@ -760,6 +897,50 @@ void morphocuda_initialize(void) {
         fprintf(stderr, "[morphocuda] CUDA unavailable (%s): functionals stay on the reference builtins\n", mcu_last_error());
         return;
     }
+    int nhooks = 0;
+    /* (1) generic pass: flush device-resident arguments before any builtin that is not accelerated */
+    const char *rmin = getenv("MORPHO_CUDA_RESIDENT_MIN");
+    if (rmin) mc_resident_min = atol(rmin);
+    bool resident = mc_resident_min >= 0 && !mc_paranoid;
+    if (!resident) mc_resident_min = 0x7fffffffffffL;
+    if (resident) nhooks += hook_everything();
+    /* (2) writers: what they invalidate */
+    nhooks += hook_method("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF, resident ? ACC_ASSIGN : ACC_NONE, true);
+    nhooks += hook_writers("Matrix", MORPHO_SETINDEX_METHOD, WRAP_MATRIX_SELF);
+    nhooks += hook_method("Matrix", MATRIX_SETCOLUMN_METHOD, WRAP_MATRIX_SELF, resident ? ACC_SETCOLUMN : ACC_NONE, true);
+    nhooks += hook_method("Matrix", MATRIX_SETCOLUMN_METHOD_DEPRECATED, WRAP_MATRIX_SELF, resident ? ACC_SETCOLUMN : ACC_NONE, true);
+    nhooks += hook_method("Matrix", MORPHO_ACC_METHOD, WRAP_MATRIX_SELF, resident ? ACC_ACC : ACC_NONE, true);
+    nhooks += hook_writers("Matrix", MATRIX_RESHAPE_METHOD, WRAP_MATRIX_RESHAPE);
+    nhooks += hook_writers("Mesh", MESH_SETVERTEXPOSITION_METHOD, WRAP_MESH_VERTS);
+    nhooks += hook_method("Mesh", MESH_SETVERTEXMATRIX_METHOD, WRAP_MESH_VERTS, ACC_NONE, false);      /* swaps a pointer, reads nothing */
+    nhooks += hook_writers("Mesh", MESH_ADDGRADE_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_REMOVEGRADE_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_RESETCONNECTIVITY_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Mesh", MESH_ADDSYMMETRY_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Sparse", SPARSE_SETROWINDICES_METHOD, WRAP_CONN_ALL);
+    nhooks += hook_writers("Sparse", MORPHO_SETINDEX_METHOD, WRAP_CONN_ALL);
+    /* (3) the Matrix methods of optimize.morpho's line searches, on device-resident matrices (mc_resident.h) */
+    if (resident) {
+        hook_method("Matrix", MORPHO_ADD_METHOD, WRAP_NONE, ACC_ADD, true);
+        hook_method("Matrix", MORPHO_ADDR_METHOD, WRAP_NONE, ACC_ADDR, true);
+        hook_method("Matrix", MORPHO_SUB_METHOD, WRAP_NONE, ACC_SUB, true);
+        hook_method("Matrix", MORPHO_SUBR_METHOD, WRAP_NONE, ACC_SUBR, true);
+        hook_method("Matrix", MORPHO_MUL_METHOD, WRAP_NONE, ACC_MUL, true);
+        hook_method("Matrix", MORPHO_MULR_METHOD, WRAP_NONE, ACC_MULR, true);
+        hook_method("Matrix", MORPHO_DIV_METHOD, WRAP_NONE, ACC_DIV, true);
+        hook_method("Matrix", MORPHO_CLONE_METHOD, WRAP_NONE, ACC_CLONE, true);
+        hook_method("Matrix", MATRIX_INNER_METHOD, WRAP_NONE, ACC_INNER, true);
+        hook_method("Matrix", MATRIX_NORM_METHOD, WRAP_NONE, ACC_NORM, true);
+        hook_method("Matrix", MORPHO_SUM_METHOD, WRAP_NONE, ACC_SUM, true);
+        hook_method("Matrix", MATRIX_GETCOLUMN_METHOD, WRAP_NONE, ACC_GETCOLUMN, true);
+        hook_method("Matrix", MORPHO_COUNT_METHOD, WRAP_NONE, ACC_NONE, false);            /* metadata only */
+        hook_method("Matrix", MATRIX_DIMENSIONS_METHOD, WRAP_NONE, ACC_NONE, false);
+        hook_method("Mesh", MESH_VERTEXMATRIX_METHOD, WRAP_NONE, ACC_NONE, false);         /* returns the object */
+        hook_method("Mesh", MORPHO_COUNT_METHOD, WRAP_NONE, ACC_NONE, false);
+        hook_method("Mesh", MESH_MAXGRADE_METHOD, WRAP_NONE, ACC_NONE, false);
+    }
+
+    /* (4) the functionals themselves; the saved originals are the trampolines of (1): flush, then the reference builtin */
     int npatched = 0;
     PATCH(Length, total); PATCH(Length, integrand); PATCH(Length, gradient);
     PATCH(Area, total); PATCH(Area, integrand); PATCH(Area, gradient);
@@ -775,27 +956,14 @@ void morphocuda_initialize(void) {
     PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
     PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
 
-    int nhooks = 0;
-    nhooks += hook_writers("Matrix", MORPHO_ASSIGN_METHOD, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Matrix", MORPHO_SETINDEX_METHOD, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Matrix", MATRIX_SETCOLUMN_METHOD, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Matrix", MATRIX_SETCOLUMN_METHOD_DEPRECATED, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Matrix", MORPHO_ACC_METHOD, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Matrix", MATRIX_RESHAPE_METHOD, WRAP_MATRIX_SELF);
-    nhooks += hook_writers("Mesh", MESH_SETVERTEXPOSITION_METHOD, WRAP_MESH_VERTS);
-    nhooks += hook_writers("Mesh", MESH_SETVERTEXMATRIX_METHOD, WRAP_MESH_VERTS);
-    nhooks += hook_writers("Mesh", MESH_ADDGRADE_METHOD, WRAP_MESH_CONN);
-    nhooks += hook_writers("Mesh", MESH_REMOVEGRADE_METHOD, WRAP_MESH_CONN);
-    nhooks += hook_writers("Mesh", MESH_RESETCONNECTIVITY_METHOD, WRAP_MESH_CONN);
-    nhooks += hook_writers("Mesh", MESH_ADDSYMMETRY_METHOD, WRAP_MESH_CONN);
-    nhooks += hook_writers("Sparse", SPARSE_SETROWINDICES_METHOD, WRAP_CONN_ALL);
-    nhooks += hook_writers("Sparse", MORPHO_SETINDEX_METHOD, WRAP_CONN_ALL);
-
     object probe;
     memset(&probe, 0, sizeof(probe));
     probe.type = OBJECT_MESH;
     objecttypedefn *defn = object_getdefn(&probe);
     if (defn && defn->freefn != mc_meshfree) { orig_meshfree = defn->freefn; defn->freefn = mc_meshfree; }
+    probe.type = OBJECT_MATRIX;
+    defn = object_getdefn(&probe);
+    if (resident && defn && defn->freefn != mc_matrixfree) { orig_matrixfree = defn->freefn; defn->freefn = mc_matrixfree; }
 
     mc_ready = true;
     if (mc_verbose) fprintf(stderr, "[morphocuda] ready: %d builtins re-pointed, %d writers hooked\n", npatched, nhooks);
@@ -803,6 +971,7 @@ void morphocuda_initialize(void) {
 
 void morphocuda_finalize(void) {
     mc_ready = false;
+    while (nshadows > 0) shadow_drop(&shadows[nshadows - 1]);
     while (nmirrors > 0) mirror_drop(nmirrors - 1);
     fields_drop_for(NULL);
     mcu_finalize();

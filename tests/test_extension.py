@@ -54,7 +54,7 @@ def test_extension_loads_and_is_inert_without_a_gpu(tmp_path):
     ref, _ = run(src, tmp_path, "stock.morpho")
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho")
     assert "CUDA unavailable" in err                 # loud, and nothing of ours computes on the CPU
-    assert new[-1].replace(" ", "") == "[0,0,0,0,0,0]"
+    assert new[-1].replace(" ", "") == "[0,0,0,0,0,0,0,0,0,0]"
     assert ref == new[:-1]
 
 
@@ -153,6 +153,30 @@ def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):
         assert vert_uploads < evals, stats
     if name == "field_functionals.morpho":
         assert fallbacks == 0 and field_uploads > 0, stats       # every call of the script ran on the GPU
+
+
+@pytest.mark.gpu
+def test_device_resident_matrices_are_coherent(tmp_path):
+    """SURVEY 8f N1 (morpho_b200/ext/mc_resident.h): with MORPHO_CUDA_RESIDENT_MIN=1 every Matrix of the script lives on
+    the device; acc / clone / inner / norm / sum / + - * / / setcolumn / column / assign run as kernels, everything else
+    (element access, transpose, reshape, block constructors, printing, Mesh.setvertexposition) sees a host copy that is
+    brought up to date first.  Every printed number agrees with the stock reference; a whole line-search step moves no
+    matrix across PCIe."""
+    src = script("resident_ops.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho",
+                   {"MORPHO_CUDA_VERBOSE": "1", "MORPHO_CUDA_RESIDENT_MIN": "1"})
+    assert "ready:" in err, err
+    stats = [float(x) for x in NUM.findall(new[-1])]
+    evals, fallbacks, devops, flushes = stats[0], stats[3], stats[6], stats[7]
+    assert evals > 30 and fallbacks == 0 and devops > 150, (stats, err)
+    i = [k for k, l in enumerate(ref) if l.startswith("energy")][0]
+    compare(ref[:i], new[:i], 1e-12)
+    compare(ref[i:], new[i:-1], 1e-10)          # 7 optimiser iterations with line searches
+    # default threshold: the same script, matrices too small to be shadowed, behaves as in round 1
+    new2, _ = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext2.morpho")
+    assert [float(x) for x in NUM.findall(new2[-1])][6] == 0
+    compare(ref[:i], new2[:i], 1e-12)
 
 
 EXAMPLES = os.path.join(REF, "examples")
