@@ -253,6 +253,12 @@ class PeerExchange:
             self._ptrs[i] = g.data_ptr()
         self._lib.check(self.L.mcu_halo_exchange(self.h, len(grads), self._ptrs, self.dim))
 
+    def exchange_ptrs(self, *dev_ptrs):
+        """The same for raw device pointers (gradients held in mcu_matrix objects)."""
+        for i, p in enumerate(dev_ptrs):
+            self._ptrs[i] = p
+        self._lib.check(self.L.mcu_halo_exchange(self.h, len(dev_ptrs), self._ptrs, self.dim))
+
     def attach(self, mesh):
         """Fused mode: the patch gradient kernel of ``mesh`` pushes the shared rows itself; call
         ``bind(slot)`` before evaluating the gradient that occupies column block ``slot``."""
