@@ -337,20 +337,49 @@ def run_ours(args):
     if world > 1:
         from morpho_b200.partition import PeerExchange
         exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
-        if not args.no_fused_push:
+        if not args.no_fused_push and args.exchange != "nccl":
             exch.attach(mesh)                             # the gradient kernels store the shared rows into the peers' buffers themselves
 
-    fused = exch is not None and not args.no_fused_push
+    fused = exch is not None and not args.no_fused_push and args.exchange != "nccl"
 
-    def step_device():
+    nccl_state = {}
+
+    def nccl_exchange():
+        """Comparison arm (--exchange nccl): ONE ncclAllReduce of the packed rows of all shared vertices (zero where this
+        rank does not hold the vertex), then unpack — the collective-library way to do what mcu_halo.cu does."""
+        if not nccl_state:
+            nccl_state["idx"] = torch.as_tensor(part.shared_local, dtype=torch.int64, device="cuda")
+            nccl_state["slot"] = torch.as_tensor(part.shared_slot, dtype=torch.int64, device="cuda")
+            nccl_state["buf"] = torch.zeros((part.n_slots, 6), dtype=torch.float64, device="cuda")
+        idx, slot, buf = nccl_state["idx"], nccl_state["slot"], nccl_state["buf"]
+        buf.zero_()
+        buf.index_copy_(0, slot, torch.cat([g_area.view(-1, 3).index_select(0, idx), g_vol.view(-1, 3).index_select(0, idx)], dim=1))
+        dist.all_reduce(buf)
+        rows = buf.index_select(0, slot)
+        g_area.view(-1, 3).index_copy_(0, idx, rows[:, :3].contiguous())
+        g_vol.view(-1, 3).index_copy_(0, idx, rows[:, 3:].contiguous())
+
+    def step_device(evs=None):
+        if evs: evs[0].record(stream)
         if fused:
             exch.bind(0)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
+        if exch is not None and args.exchange == "overlap":
+            exch.exchange_async(0, g_area.data_ptr())     # Area's shared rows complete underneath the next kernel
+        if evs: evs[1].record(stream)
         if fused:
             exch.bind(1)
         _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
+        if evs: evs[2].record(stream)
         if exch is not None:
-            exch(g_area, g_vol)                   # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
+            if args.exchange == "overlap":
+                exch.exchange_async(1, g_vol.data_ptr())
+                exch.join()
+            elif args.exchange == "nccl":
+                nccl_exchange()
+            else:
+                exch(g_area, g_vol)               # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
+        if evs: evs[3].record(stream)
 
     def barrier():
         if world > 1:
@@ -380,18 +409,7 @@ def run_ours(args):
     barrier()
     e_start.record(stream)
     for k in range(args.steps):
-        ev[k][0].record(stream)
-        if fused:
-            exch.bind(0)
-        _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
-        ev[k][1].record(stream)
-        if fused:
-            exch.bind(1)
-        _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
-        ev[k][2].record(stream)
-        if exch is not None:
-            exch(g_area, g_vol)
-        ev[k][3].record(stream)
+        step_device(ev[k])
     e_end.record(stream)
     barrier()
     launches = L.mcu_launch_count() - launches0
@@ -478,10 +496,15 @@ def run_ours(args):
         if fused:
             exch.bind(0)
         _lib.check(L.mcu_eval_matrix(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, GA))
+        if exch is not None and args.exchange == "overlap":
+            exch.exchange_async(0, L.mcu_matrix_device(GA))
         if fused:
             exch.bind(1)
         _lib.check(L.mcu_eval_matrix(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, GV))
-        if exch is not None:
+        if exch is not None and args.exchange == "overlap":
+            exch.exchange_async(1, L.mcu_matrix_device(GV))
+            exch.join()
+        elif exch is not None:
             exch.exchange_ptrs(L.mcu_matrix_device(GA), L.mcu_matrix_device(GV))
         _lib.check(L.mcu_mesh_status(mesh._h))                                                          # degenerate / VolEnclZero of the gradients
 
@@ -530,7 +553,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_string(f, world), "inputs": INPUTS,
-                   "partition": "contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) and summed in rank order" if world > 1 else "single GPU",
+                   "partition": ("contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) "
+                                 f"and summed in rank order; exchange mode: {args.exchange}") if world > 1 else "single GPU",
                    "gradient_path": "persistent patch kernel: bulk-async (TMA) staging of vertex runs into a 3-stage shared-memory ring, one consumer thread per owned vertex walks its ring (owner computes, no atomics)",
                    "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol, "shared_row_exchange": ms_exch if world > 1 else 0.0}},
         "clocks": clocks,
@@ -579,6 +603,9 @@ def main():
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "serial", "nccl"],
+                    help="multi-GPU completion of shared rows: peer-memory exchange on a second stream underneath the gradient kernels "
+                         "(default), the same exchange serialised behind them, or one ncclAllReduce of the packed rows (comparison)")
     ap.add_argument("--no-fused-push", action="store_true", help="multi-GPU: push the shared rows in the exchange kernel instead of the gradient kernels")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -253,7 +253,8 @@ int mcu_binbounds(int nel, int nbins, int *bounds);
 /* ---- multi-GPU (one process per GPU): completion of the gradient rows of vertices shared between ranks.
  *      Elements are partitioned in contiguous id ranges (mcu_binbounds); the reference's analogue is the merge of the
  *      per-thread gradient matrices with matrix_axpy (functional.c:1106-1119).  The exchange runs over NVLink peer
- *      memory (CUDA IPC), not through a collective library: see morpho_b200/csrc/mcu_halo.cu.
+ *      memory (CUDA IPC), not through a collective library: see morpho_b200/csrc/mcu_halo.cu.  At most 16 ranks, 4
+ *      gradients (column blocks) per step.
  *        shared_local[n_shared]        local ids of the vertices other ranks also touch, ascending global id
  *        peer_ptr[world+1], peer_pos[] per peer q the positions (in shared_local) of the vertices shared with q,
  *                                      ascending global id — the same order on both sides of a pair
@@ -269,6 +270,11 @@ mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_shared, const in
 int mcu_halo_export(mcu_halo *h, unsigned char handle[64]);          /* IPC handle of this rank's receive block */
 int mcu_halo_connect(mcu_halo *h, const unsigned char *handles);     /* world x 64 bytes, rank order */
 int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim);   /* asynchronous, library stream */
+/* one gradient (column block `slot`) on the library's SECOND stream, underneath the kernels queued on the library stream;
+ * mcu_halo_join makes the library stream wait for the exchanges in flight (implied by the next evaluation of the same
+ * column block on the attached mesh, by mcu_halo_exchange and by mcu_halo_status) */
+int mcu_halo_exchange_async(mcu_halo *h, int slot, double *dev_grad, int dim);
+int mcu_halo_join(mcu_halo *h);
 /* fused mode: the patch gradient kernel of `m` stores the shared rows into the peers' buffers itself (column block
  * `slot` of the exchanged row, chosen with mcu_halo_bind before each evaluation); mcu_halo_exchange then only raises
  * the flags, waits for the peers and combines */

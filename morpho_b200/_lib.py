@@ -125,6 +125,8 @@ def lib():
         "mcu_halo_export": (C.c_int, [vp, vp]),
         "mcu_halo_connect": (C.c_int, [vp, vp]),
         "mcu_halo_exchange": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "mcu_halo_exchange_async": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "mcu_halo_join": (C.c_int, [vp]),
         "mcu_halo_status": (C.c_int, [vp]),
         "mcu_halo_attach": (C.c_int, [vp, vp]),
         "mcu_halo_bind": (C.c_int, [vp, C.c_int]),

@@ -6,18 +6,26 @@
 // gradient rows for the vertices its elements touch; rows of vertices touched by several ranks have to be summed.
 //
 // No collective library call sits on this path.  Every rank owns one device block
-//     [ flags: int[world] | recv[2][world][max_m][ncomp] doubles ]
-// exported with cudaIpcGetMemHandle and mapped by all peers (NVLink / NVSwitch P2P):
-//   k_halo_exchange (ONE launch per exchange)
-//     push     each (peer q, k) pair stores this rank's partial row of the k-th vertex shared with q straight into
-//              q's recv[parity][rank][k] (remote stores); the last CTA to finish fences and raises flags[rank] = epoch
-//              on every peer;
-//     combine  waits until all peers' flags reached the epoch, then sums, per shared vertex, the contributions of all
-//              sharing ranks in ASCENDING RANK ORDER (own partial included at its place) and writes the completed row
-//              back — the same order on every rank, so shared rows end up bitwise identical everywhere and the
-//              result is deterministic.
-// Two receive buffers alternate (parity = epoch & 1): a rank can be at most one exchange ahead of a peer, because
-// finishing exchange e needs every peer's flag e, which a peer raises only after it finished combining e-1.
+//     [ control words (MCU_HALO_CTRL_BYTES) | recv[2][world][max_m][ncomp] doubles ]
+// exported with cudaIpcGetMemHandle and mapped by all peers (NVLink / NVSwitch P2P).  A row carries one COLUMN BLOCK
+// ("slot") per gradient exchanged in a step (Area: columns 0..2, VolumeEnclosed: 3..5); every slot has its own flags and
+// its own device-side epoch counter, so the exchange of one gradient is independent of the other's:
+//   push     this rank's partial row of the k-th vertex shared with peer q is stored straight into q's
+//            recv[parity][rank][k] (remote stores) — by the patch gradient kernel itself (fused mode: the patches that own
+//            shared vertices are handed out FIRST, and the last of them to finish raises flags[slot][rank] = epoch on
+//            every peer and the local "own rows written" word, long before the kernel ends), or by k_halo_slot when the
+//            gradient came from another kernel;
+//   combine  k_halo_slot waits until the peers' flags (and, fused, the local word) reached the epoch, then sums, per
+//            shared vertex, the contributions of all sharing ranks in ASCENDING RANK ORDER (own partial included at its
+//            place) and writes the completed row back — the same order on every rank, so shared rows end up bitwise
+//            identical everywhere and the result is deterministic; the last CTA to finish bumps the slot's epoch.
+// k_halo_slot is a grid of single-warp CTAs with <= 32 registers: such a CTA fits beside two resident CTAs of the
+// persistent patch kernel on every SM, so on the library's SECOND STREAM (mcu_halo_exchange_async) the whole exchange of
+// one gradient runs underneath the gradient kernels and costs the step only the final join.
+// Two receive buffers alternate (parity = epoch & 1): a rank can be at most one exchange of a slot ahead of a peer,
+// because finishing exchange e needs every peer's flag e, which a peer raises from its gradient kernel of step e, which is
+// stream-ordered behind the peer's combine of e-1.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -29,7 +37,6 @@ extern long g_mcu_launches;
 
 struct mcu_halo {
     int rank = 0, world = 1, ncomp = 0, n_shared = 0, max_m = 0, n_pairs = 0;
-    int epoch = 0;
     // plan (device)
     int *d_shared_local = nullptr;   // n_shared local vertex ids (ascending global id)
     int *d_peer_ptr = nullptr;       // world+1 offsets into d_peer_pos
@@ -42,89 +49,95 @@ struct mcu_halo {
     size_t block_bytes = 0, recv_off = 0;
     std::vector<void *> peer_block;  // world pointers (own block at [rank])
     void **d_peer_block = nullptr;   // device copy
-    unsigned *d_counter = nullptr;
+    unsigned *d_counter = nullptr;   // per slot: CTAs past the push phase [slot], CTAs finished [4 + slot]
     unsigned *d_status = nullptr;    // bit 0: a peer did not show up in time
     // host copies of the pair lists (for mcu_halo_attach) and the fused mode switch
     std::vector<int> h_shared_local, h_peer_ptr, h_peer_pos;
-    bool fused = false;              // pushes ride in the patch gradient kernel; the exchange kernel only combines
-    unsigned pushed_mask = 0;        // fused mode: column blocks (slots) a gradient kernel pushed since the last exchange
+    bool fused = false;              // pushes ride in the patch gradient kernel; k_halo_slot only combines
+    unsigned pushed_mask = 0;        // fused mode: column blocks (slots) a gradient kernel pushed since their last exchange
     long long timeout_cycles = 240000000000LL;   // ~2 minutes at 1.9 GHz (option "halo_timeout_ms")
     bool failed = false;             // a peer timed out in an earlier exchange: reported by the next call
     mcu_mesh *mesh = nullptr;
+    // second stream: exchanges that run underneath the gradient kernels (mcu_halo_exchange_async / mcu_halo_join)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side[MCU_HALO_MAXSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    bool side_pending[MCU_HALO_MAXSLOT] = {false, false, false, false};
 };
 
-#define HALO_MAXGRAD 4
-struct HaloGrads {
-    double *g[HALO_MAXGRAD];
-};
+extern "C" int mcu_halo_join(mcu_halo *h);
+static int halo_join_slot(mcu_halo *h, int slot);
 
-// One launch per exchange.  Phase 1 (push): every (peer q, k) pair stores this rank's partial row of the k-th vertex
-// shared with q straight into q's recv[parity][rank][k] (remote stores); one system-scope fence per CTA, and the last
-// CTA to get there raises flags[rank] = epoch on every peer.  Phase 2 (combine): every CTA waits until all peers'
-// flags reached the epoch — peers raise them independently of this grid, and the grid is small enough (<= 64 CTAs)
-// to be resident as a whole — then sums its share of the shared vertices in ascending rank order.
-__global__ void __launch_bounds__(256)
-k_halo_exchange(HaloGrads grads, int ngrad, int dim, const int *__restrict__ shared_local,
-                const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
-                const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank, const int *__restrict__ contrib_k,
-                unsigned char *block, size_t recv_off, int rank, int world, int max_m, int ncomp, int parity, int n_pairs,
-                int n_shared, unsigned *counter, unsigned *status, int epoch, long long timeout_cycles) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += gridDim.x * blockDim.x) {
-        int q = 0;
-        while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
-        int k = t - peer_ptr[q];
-        int v = shared_local[peer_pos[t]];
-        double *dst = (double *) ((unsigned char *) peer_block[q] + recv_off) +
-                      (((size_t) parity * world + rank) * max_m + k) * ncomp;
-        for (int gi = 0; gi < ngrad; gi++)
-            for (int c = 0; c < dim; c++) dst[gi * dim + c] = grads.g[gi][(size_t) v * dim + c];   // remote stores
-    }
-    __syncthreads();
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        // n_pairs == 0 (fused mode): the rows were stored by the gradient kernels, which have completed; nothing of
-        // this grid has to be ordered before the flags, so one CTA raises them right away.
-        bool raise = (n_pairs == 0) ? (blockIdx.x == 0) : false;
-        if (n_pairs > 0) {
-            __threadfence_system();                    // cumulative: covers the block's stores ordered by the barrier
-            unsigned done = atomicAdd(counter, 1u);
-            if (done == gridDim.x - 1) { *counter = 0; raise = true; }
+#define HALO_WARPS_MAX 296           // single-warp CTAs: two per SM
+
+// One launch per (exchange, slot).  Single-warp CTAs.
+__global__ void __maxnreg__(32)
+k_halo_slot(double *__restrict__ grad, int dim, int slot, const int *__restrict__ shared_local,
+            const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
+            const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank, const int *__restrict__ contrib_k,
+            unsigned char *block, size_t recv_off, int rank, int world, int max_m, int ncomp, int n_pairs,
+            int n_shared, unsigned *counter, unsigned *status, int wait_own, long long timeout_cycles) {
+    volatile int *ctrl = (volatile int *) block;
+    // the epoch cannot move while any CTA of this launch is alive: it is bumped by the LAST CTA to finish
+    const int epoch = ctrl[MCU_HALO_EPOCH(slot)] + 1;
+    const int parity = epoch & 1;
+    const int col0 = slot * dim;
+    const int lane = threadIdx.x;
+    if (n_pairs > 0) {
+        // push phase (the gradient did not come from the fused patch kernel): this launch is stream-ordered behind it
+        for (int t = blockIdx.x * 32 + lane; t < n_pairs; t += gridDim.x * 32) {
+            int q = 0;
+            while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
+            const int k = t - peer_ptr[q];
+            const int v = shared_local[peer_pos[t]];
+            double *dst = (double *) ((unsigned char *) peer_block[q] + recv_off) + (((size_t) parity * world + rank) * max_m + k) * ncomp + col0;
+            for (int c = 0; c < dim; c++) dst[c] = grad[(size_t) v * dim + c];   // remote stores
         }
-        if (raise) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && atomicAdd(counter + slot, 1u) == gridDim.x - 1) {
+            counter[slot] = 0;
             __threadfence_system();
             for (int q = 0; q < world; q++)
-                if (q != rank) ((volatile int *) peer_block[q])[rank] = epoch;    // "my rows of exchange `epoch` have landed"
+                if (q != rank) ((volatile int *) peer_block[q])[MCU_HALO_FLAG(slot, rank)] = epoch;    // "my rows of exchange `epoch` have landed"
         }
-        volatile int *flags = (volatile int *) block;
-        int good = 1;
-        long long t0 = clock64();
+    }
+    int good = 1;
+    if (lane == 0) {
+        const long long t0 = clock64();
+        if (wait_own) while (ctrl[MCU_HALO_OWNDONE(slot)] < epoch) { if (clock64() - t0 > timeout_cycles) { good = 0; break; } __nanosleep(40); }
         for (int q = 0; q < world && good; q++) {
-            if (q == rank) continue;
-            while (flags[q] < epoch) {
-                if (clock64() - t0 > timeout_cycles) { good = 0; break; }   // a peer is gone; do not hang the GPU
-                __nanosleep(20);
+            if (q == rank || peer_ptr[q + 1] == peer_ptr[q]) continue;        // nothing shared with q
+            while (ctrl[MCU_HALO_FLAG(slot, q)] < epoch) {
+                if (clock64() - t0 > timeout_cycles) { good = 0; break; }      // a peer is gone; do not hang the GPU
+                __nanosleep(40);
             }
         }
-        // acquire side: order the flag observation before the (cache-bypassing, ld.cv) reads of the received rows
-        // that the other threads issue after the barrier below
+        // acquire side: order the flag observations before the (cache-bypassing) reads of the rows below
         __threadfence_system();
-        ok = good;
         if (!good) atomicOr(status, 1u);
     }
-    __syncthreads();
-    if (!ok) return;
-    const double *recv = (const double *) (block + recv_off);
-    const int ncols = ngrad * dim;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_shared * ncols; t += gridDim.x * blockDim.x) {
-        int i = t / ncols, col = t - i * ncols, gi = col / dim, c = col - gi * dim;
-        int v = shared_local[i];
-        double own = grads.g[gi][(size_t) v * dim + c], sum = 0.0;
-        for (int j = contrib_ptr[i]; j < contrib_ptr[i + 1]; j++) {
-            int q = contrib_rank[j], k = contrib_k[j];
-            double x = (k < 0) ? own : __ldcv(recv + (((size_t) parity * world + q) * max_m + k) * ncomp + col);
-            sum = __dadd_rn(sum, x);                  // ascending rank order, identical on every sharing rank
+    good = __shfl_sync(0xffffffffu, good, 0);
+    if (good) {
+        const double *recv = (const double *) (block + recv_off);
+        for (int t = blockIdx.x * 32 + lane; t < n_shared * dim; t += gridDim.x * 32) {
+            const int i = t / dim, c = t - i * dim;
+            const int v = shared_local[i];
+            const double own = __ldcv(grad + (size_t) v * dim + c);
+            double sum = 0.0;
+            for (int j = contrib_ptr[i]; j < contrib_ptr[i + 1]; j++) {
+                const int q = contrib_rank[j], k = contrib_k[j];
+                const double x = (k < 0) ? own : __ldcv(recv + (((size_t) parity * world + q) * max_m + k) * ncomp + col0 + c);
+                sum = __dadd_rn(sum, x);                  // ascending rank order, identical on every sharing rank
+            }
+            grad[(size_t) v * dim + c] = sum;
         }
-        grads.g[gi][(size_t) v * dim + c] = sum;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && atomicAdd(counter + 4 + slot, 1u) == gridDim.x - 1) {
+        counter[4 + slot] = 0;
+        __threadfence();
+        ctrl[MCU_HALO_EPOCH(slot)] = epoch;               // this exchange of the slot is complete
     }
 }
 
@@ -151,7 +164,8 @@ extern "C" mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_share
     h->d_contrib_ptr = upload_ints(contrib_ptr, (size_t) n_shared + 1);
     h->d_contrib_rank = upload_ints(contrib_rank, (size_t) contrib_ptr[n_shared]);
     h->d_contrib_k = upload_ints(contrib_k, (size_t) contrib_ptr[n_shared]);
-    h->recv_off = 256;
+    if (world > MCU_HALO_MAXWORLD) { mcu_set_error("halo: at most %d ranks", MCU_HALO_MAXWORLD); delete h; return nullptr; }
+    h->recv_off = MCU_HALO_CTRL_BYTES;
     h->block_bytes = h->recv_off + sizeof(double) * 2 * (size_t) world * (size_t) (max_m ? max_m : 1) * ncomp;
     bool ok = h->d_shared_local && h->d_peer_ptr && h->d_peer_pos && h->d_contrib_ptr && h->d_contrib_rank && h->d_contrib_k &&
               cudaMalloc((void **) &h->d_block, h->block_bytes) == cudaSuccess &&
@@ -159,7 +173,15 @@ extern "C" mcu_halo *mcu_halo_create(int rank, int world, int ncomp, int n_share
               cudaMalloc((void **) &h->d_counter, 64) == cudaSuccess && cudaMemset(h->d_counter, 0, 64) == cudaSuccess &&
               cudaMalloc((void **) &h->d_peer_block, sizeof(void *) * world) == cudaSuccess;
     if (!ok) { mcu_set_error("halo allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete h; return nullptr; }
-    h->d_status = h->d_counter + 4;
+    h->d_status = h->d_counter + 12;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side[3], cudaEventDisableTiming) != cudaSuccess) {
+        mcu_set_error("halo: stream / event creation failed"); delete h; return nullptr;
+    }
     h->peer_block.assign((size_t) world, nullptr);
     h->peer_block[rank] = h->d_block;
     return h;
@@ -190,44 +212,90 @@ extern "C" int mcu_halo_connect(mcu_halo *h, const unsigned char *handles) {
     return MCU_OK;
 }
 
-extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim) {
-    if (!h || ngrad < 1 || ngrad > HALO_MAXGRAD || ngrad * dim > h->ncomp) { mcu_set_error("bad halo exchange arguments"); return MCU_ERR_ARGS; }
-    if (h->world == 1) return MCU_OK;
-    if (h->failed) { mcu_set_error("halo exchange: a peer did not arrive in time in an earlier exchange"); return MCU_ERR_CUDA; }
-    // fused mode: the exchange kernel may skip its push phase only when a gradient kernel really pushed every column
-    // block of this exchange (mcu_halo_push_params was taken for slots 0..ngrad-1 since the last exchange).  Any other
-    // route to the gradients (gather path on small meshes, selections, other functionals, a slot out of range, a
-    // patch set freed by mcu_mesh_set_connectivity) leaves rows un-pushed: push them here.
-    const unsigned want = (ngrad >= 32) ? 0xffffffffu : ((1u << ngrad) - 1u);
-    const bool all_pushed = h->fused && (h->pushed_mask & want) == want;
-    h->pushed_mask = 0;
+static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cudaStream_t st) {
+    const bool pushed = h->fused && slot < 32 && (h->pushed_mask & (1u << slot));
+    if (slot < 32) h->pushed_mask &= ~(1u << slot);
     {
         long ms = mcu_opt("halo_timeout_ms", 0);
         if (ms > 0) h->timeout_cycles = (long long) ms * 2000000LL;
     }
-    HaloGrads g;
-    for (int i = 0; i < HALO_MAXGRAD; i++) g.g[i] = i < ngrad ? dev_grads[i] : nullptr;
-    cudaStream_t st = mcu_stream();
-    h->epoch++;
-    int parity = h->epoch & 1;
-    int work = h->n_pairs > h->n_shared * ngrad * dim ? h->n_pairs : h->n_shared * ngrad * dim;
-    int nb = (work + 255) / 256;
-    nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);             // small enough to be resident as a whole (the CTAs wait for peers)
-    k_halo_exchange<<<nb, 256, 0, st>>>(g, ngrad, dim, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
-                                        h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank,
-                                        h->world, h->max_m, h->ncomp, parity, all_pushed ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status,
-                                        h->epoch, h->timeout_cycles);
+    const int work = std::max(pushed ? 0 : h->n_pairs, h->n_shared * dim);
+    int nb = (work + 31) / 32;
+    nb = nb < 1 ? 1 : (nb > HALO_WARPS_MAX ? HALO_WARPS_MAX : nb);
+    // rows the fused patch kernel pushed: only wait and combine (and wait for the local rows, the launch may overtake
+    // the gradient kernel); any other route to the gradient (gather kernel on small meshes, selections, other
+    // functionals, a patch set freed by mcu_mesh_set_connectivity) leaves rows un-pushed: push them here
+    k_halo_slot<<<nb, 32, 0, st>>>(dev_grad, dim, slot, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
+                                   h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank, h->world,
+                                   h->max_m, h->ncomp, pushed ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status, pushed ? 1 : 0,
+                                   h->timeout_cycles);
     g_mcu_launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { mcu_set_error("halo launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
     return MCU_OK;
 }
 
+static int halo_check(mcu_halo *h, int ngrad, int dim) {
+    if (!h || ngrad < 1 || ngrad > MCU_HALO_MAXSLOT || ngrad * dim > h->ncomp) { mcu_set_error("bad halo exchange arguments"); return MCU_ERR_ARGS; }
+    if (h->failed) { mcu_set_error("halo exchange: a peer did not arrive in time in an earlier exchange"); return MCU_ERR_CUDA; }
+    return MCU_OK;
+}
+
+/* complete the shared rows of ngrad gradients (column blocks 0 .. ngrad-1) on the library stream */
+extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grads, int dim) {
+    int rc = halo_check(h, ngrad, dim);
+    if (rc) return rc;
+    if (h->world == 1 || h->n_shared == 0) return MCU_OK;
+    rc = mcu_halo_join(h);
+    for (int s = 0; s < ngrad && !rc; s++) rc = halo_slot_launch(h, s, dev_grads[s], dim, mcu_stream());
+    return rc;
+}
+
+/* The same for ONE gradient (column block `slot`), on the library's second stream: called right after the evaluation
+ * that produced dev_grad was queued, the exchange runs underneath that kernel and whatever is queued next on the
+ * library stream.  mcu_halo_join makes the library stream wait for the exchanges in flight (it is called implicitly by
+ * the next evaluation on the attached mesh and by mcu_halo_exchange). */
+extern "C" int mcu_halo_exchange_async(mcu_halo *h, int slot, double *dev_grad, int dim) {
+    int rc = halo_check(h, slot + 1, dim);
+    if (rc) return rc;
+    if (slot < 0 || !dev_grad) return MCU_ERR_ARGS;
+    if (h->world == 1 || h->n_shared == 0) return MCU_OK;
+    rc = halo_join_slot(h, slot);
+    if (rc) return rc;
+    const bool pushed = h->fused && slot < 32 && (h->pushed_mask & (1u << slot));
+    if (!pushed) {
+        // the rows have to be read from the finished gradient: order the second stream behind the library stream
+        if (cudaEventRecord(h->ev_main, mcu_stream()) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_main, 0) != cudaSuccess) return MCU_ERR_CUDA;
+    }
+    rc = halo_slot_launch(h, slot, dev_grad, dim, h->side);
+    if (rc == MCU_OK && cudaEventRecord(h->ev_side[slot], h->side) != cudaSuccess) rc = MCU_ERR_CUDA;
+    h->side_pending[slot] = true;
+    return rc;
+}
+
+/* the library stream waits for the exchange of `slot` that is in flight on the second stream */
+static int halo_join_slot(mcu_halo *h, int slot) {
+    if (!h->side_pending[slot]) return MCU_OK;
+    if (cudaStreamWaitEvent(mcu_stream(), h->ev_side[slot], 0) != cudaSuccess) {
+        mcu_set_error("halo join failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MCU_ERR_CUDA;
+    }
+    h->side_pending[slot] = false;
+    return MCU_OK;
+}
+
+extern "C" int mcu_halo_join(mcu_halo *h) {
+    if (!h) return MCU_ERR_ARGS;
+    int rc = MCU_OK;
+    for (int s = 0; s < MCU_HALO_MAXSLOT && !rc; s++) rc = halo_join_slot(h, s);
+    return rc;
+}
+
 /* 0 = all exchanges so far completed; 1 = a peer did not arrive in time (synchronises the stream) */
 extern "C" int mcu_halo_status(mcu_halo *h) {
     if (!h) return MCU_ERR_ARGS;
     unsigned s = 0;
-    if (cudaStreamSynchronize(mcu_stream()) != cudaSuccess) return MCU_ERR_CUDA;
+    if (mcu_halo_join(h) != MCU_OK || cudaStreamSynchronize(mcu_stream()) != cudaSuccess) return MCU_ERR_CUDA;
     if (cudaMemcpy(&s, h->d_status, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return MCU_ERR_CUDA;
     if (s) h->failed = true;             // later exchanges fail loudly instead of summing incomplete rows
     return (int) s;
@@ -266,8 +334,9 @@ bool mcu_halo_push_params(mcu_halo *h, int slot, int dim, McuHaloPush *out) {
     out->peer_block = (void *const *) h->d_peer_block;
     out->recv_off = h->recv_off;
     out->rank = h->rank; out->world = h->world; out->max_m = h->max_m; out->ncomp = h->ncomp;
-    out->parity = (h->epoch + 1) & 1;     // the exchange that follows this evaluation
+    out->slot = slot;
     out->col0 = slot * dim;
+    if (slot < MCU_HALO_MAXSLOT) halo_join_slot(h, slot);   // the previous exchange of this column block has to be through
     if (slot < 32) h->pushed_mask |= 1u << slot;
     return true;
 }
@@ -282,7 +351,11 @@ void mcu_halo_detach_mesh(mcu_mesh *m) {
 extern "C" int mcu_halo_destroy(mcu_halo *h) {
     if (!h) return MCU_OK;
     if (h->mesh && h->mesh->halo == h) h->mesh->halo = nullptr;
+    if (h->side) cudaStreamSynchronize(h->side);
     cudaStreamSynchronize(mcu_stream());
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
+    for (int i = 0; i < MCU_HALO_MAXSLOT; i++) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int q = 0; q < h->world; q++)
         if (q != h->rank && h->peer_block[q]) cudaIpcCloseMemHandle(h->peer_block[q]);
     cudaFree(h->d_shared_local); cudaFree(h->d_peer_ptr); cudaFree(h->d_peer_pos);

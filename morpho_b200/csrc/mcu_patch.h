@@ -84,12 +84,22 @@ struct McuPatchPlan {
 // Push of shared rows from inside the gradient kernel (multi-GPU): where thread `thread` of a patch stores a copy
 // of its row — receive buffer of rank `peer`, row `k` of the (this rank, peer) pair list.
 struct McuPushEntry { int thread, peer, k, pad; };
+// Layout of the control words (ints) at the start of every rank's receive block (mcu_halo.cu):
+#define MCU_HALO_MAXSLOT 4
+#define MCU_HALO_MAXWORLD 16
+#define MCU_HALO_FLAG(slot, q) ((slot) * MCU_HALO_MAXWORLD + (q))   // "rank q's rows of column block `slot` have landed": epoch
+#define MCU_HALO_OWNDONE(slot) (64 + (slot))                        // this rank's own partial rows of `slot` are written: epoch
+#define MCU_HALO_EPOCH(slot) (68 + (slot))                          // completed exchanges of `slot` (the device-side epoch)
+#define MCU_HALO_CTRL_BYTES 1024
 struct McuHaloPush {      // kernel parameter; entries == nullptr: no exchange attached
     const McuPushEntry *entries;
     const int *wptr;                 // per boundary patch 17 offsets into entries: entries of warp w = [wptr[w], wptr[w+1])
-    void *const *peer_block;         // device array: base of every rank's receive block
+    const int *order;                // hand-out order of the patches: the ones that push first
+    int *done;                       // counter of finished pushing patches (self re-arming)
+    void *const *peer_block;         // device array: base of every rank's receive block (own block at [rank])
     unsigned long long recv_off;     // byte offset of recv[][][][] in a block
-    int rank, world, max_m, ncomp, parity, col0;   // col0 = first column of this gradient in a row (slot * dim)
+    int rank, world, max_m, ncomp, slot, col0;   // col0 = first column of this gradient in a row (slot * dim)
+    int n_push_patches;              // patches with push entries: the last of them to finish raises the flags
 };
 
 struct McuPatchSet {
@@ -99,6 +109,8 @@ struct McuPatchSet {
     std::vector<int> tab_word_off;   // per patch: word offset of its table header in d_tab
     McuPushEntry *d_push = nullptr;
     int *d_push_wptr = nullptr;
+    int *d_order = nullptr;          // hand-out order with the pushing patches first (attached exchange), + the done counter behind it
+    int n_push_patches = 0;
     struct CompSum *d_partials = nullptr;   // totals: one compensated partial sum per (patch, consumer warp)
     int n_patches = 0;
     McuPatchDesc *d_desc = nullptr;

@@ -259,6 +259,13 @@ class PeerExchange:
             self._ptrs[i] = p
         self._lib.check(self.L.mcu_halo_exchange(self.h, len(dev_ptrs), self._ptrs, self.dim))
 
+    def exchange_async(self, slot, dev_ptr):
+        """One gradient (column block ``slot``) on the library's second stream: runs underneath the kernels queued next."""
+        self._lib.check(self.L.mcu_halo_exchange_async(self.h, slot, dev_ptr, self.dim))
+
+    def join(self):
+        self._lib.check(self.L.mcu_halo_join(self.h))
+
     def attach(self, mesh):
         """Fused mode: the patch gradient kernel of ``mesh`` pushes the shared rows itself; call
         ``bind(slot)`` before evaluating the gradient that occupies column block ``slot``."""

@@ -42,7 +42,7 @@ def _worker(rank, world, port, f, q):
         O = Oracle()
         errs = []
         mb.set_option("gradient_path", _lib.MCU_PATH_PATCH)
-        for rep in range(6):                           # several exchanges: alternating receive buffers, epochs
+        for rep in range(8):                           # several exchanges: alternating receive buffers, epochs
             if rep == 3:
                 ex.attach(mesh)                        # fused mode: the gradient kernel pushes the shared rows itself
             for slot, (g, cls) in enumerate(zip(grads, (mb.Area, mb.VolumeEnclosed))):
@@ -50,12 +50,40 @@ def _worker(rank, world, port, f, q):
                 if rep >= 3:
                     ex.bind(slot)
                 _lib.check(L.mcu_eval_device(mesh._h, C.byref(d), None, _lib.MCU_GRADIENT, g.data_ptr()))
-            ex(*grads)
+                if rep >= 4:                           # overlapped: this gradient's exchange runs on the second stream
+                    ex.exchange_async(slot, g.data_ptr())
+            if rep >= 4:
+                ex.join()
+            else:
+                ex(*grads)
             assert ex.status() == 0
             for g, name in zip(grads, ("Area", "VolumeEnclosed")):
                 want = O.gradient(v, {2: c}, FunctionalSpec(name))[rm.gids]
                 got = g.cpu().numpy().reshape(-1, 3)
                 errs.append(np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max())
+        # a gradient that does NOT come from the pushing patch kernel while the exchange is attached (AUTO on a mesh
+        # below patch_min_elements takes the gather kernel; so do selections and other functionals): the exchange has to
+        # notice that nothing was pushed and push the rows itself — synchronously and on the second stream
+        mb.set_option("gradient_path", _lib.MCU_PATH_AUTO)
+        mb.set_option("patch_min_elements", 10 ** 9)
+        for mode in ("serial", "overlap"):
+            for slot, (g, cls) in enumerate(zip(grads, (mb.Area, mb.VolumeEnclosed))):
+                d = cls()._desc()
+                ex.bind(slot)
+                g.zero_()
+                _lib.check(L.mcu_eval_device(mesh._h, C.byref(d), None, _lib.MCU_GRADIENT, g.data_ptr()))
+                if mode == "overlap":
+                    ex.exchange_async(slot, g.data_ptr())
+            if mode == "overlap":
+                ex.join()
+            else:
+                ex(*grads)
+            assert ex.status() == 0
+            for g, name in zip(grads, ("Area", "VolumeEnclosed")):
+                want = O.gradient(v, {2: c}, FunctionalSpec(name))[rm.gids]
+                got = g.cpu().numpy().reshape(-1, 3)
+                errs.append(np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max())
+        mb.set_option("patch_min_elements", 4096)
         # energies: per-rank totals (patch kernel) summed in rank order
         from morpho_b200.partition import reduce_total
         for cls, name in ((mb.Area, "Area"), (mb.VolumeEnclosed, "VolumeEnclosed")):
