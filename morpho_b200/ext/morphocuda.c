@@ -63,7 +63,7 @@ typedef struct {
 
 static mc_mirror mirrors[MC_MAXMIRRORS];
 static int nmirrors = 0;
-static bool mc_ready = false, mc_paranoid = false, mc_verbose = false;
+static bool mc_ready = false, mc_paranoid = false, mc_verbose = false, mc_dry = false;
 static long mc_stat_evals = 0, mc_stat_vert_uploads = 0, mc_stat_conn_uploads = 0, mc_stat_fallbacks = 0;
 
 static void mc_log(const char *what, const char *detail) {
@@ -654,6 +654,8 @@ MC_FUNCTIONAL(Volume, MCU_F_VOLUME, MESH_GRADE_VOLUME)
 MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, total, MCU_TOTAL)
 MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, integrand, MCU_INTEGRAND)
 
+#include "mc_pairwise.h"
+
 /* ------------------------------------------------------------------ hooks on the VM's builtins */
 
 /* Every builtin the extension does not replace outright passes through a numbered trampoline:
@@ -668,6 +670,7 @@ static int nwraps = 0;
 
 static value wrap_call(int slot, vm *v, int nargs, value *args) {
     value self = MORPHO_SELF(args), r;
+    pairwise_scan(v);
     if (wraps[slot].accel != ACC_NONE && accel_call(wraps[slot].accel, v, nargs, args, &r)) return r;
     if (wraps[slot].flush) shadow_flush_args(nargs, args);
     /* resolve the target BEFORE the call (the method may free or replace things), mark AFTER it */
@@ -886,22 +889,27 @@ static value mc_translate_fn(vm *v, int nargs, value *args) {
 
 #define PATCH(cls, meth) npatched += patch_method(#cls, #meth, mc_##cls##_##meth, &orig_##cls##_##meth)
 
-void morphocuda_initialize(void) {
+/* Everything that is done once per process, whichever of `import morphocuda` / `import functionals` comes first. */
+static bool mc_core_done = false;
+static void mc_core_initialize(void) {
+    if (mc_core_done) return;
+    mc_core_done = true;
     const char *dev = getenv("MORPHO_CUDA_DEVICE");
     mc_paranoid = getenv("MORPHO_CUDA_PARANOID") && atoi(getenv("MORPHO_CUDA_PARANOID")) != 0;
     mc_verbose = getenv("MORPHO_CUDA_VERBOSE") && atoi(getenv("MORPHO_CUDA_VERBOSE")) != 0;
-    builtin_addfunction("cudastats", mc_stats, MORPHO_FN_ALLOCATES);
-    builtin_addfunction("cudatranslate", mc_translate_fn, MORPHO_FN_ALLOCATES);
     if (mcu_init(dev ? atoi(dev) : 0) != MCU_OK) {
         /* no CPU path of ours exists: without a usable GPU nothing is patched and the reference runs as shipped */
         fprintf(stderr, "[morphocuda] CUDA unavailable (%s): functionals stay on the reference builtins\n", mcu_last_error());
-        return;
+        /* MORPHO_CUDA_DRYHOOKS=1 (tests of the host logic on a machine without a GPU): install the trampolines and the
+         * class patch anyway; every veneer sees mc_ready == false and hands over to the reference's code */
+        if (!(getenv("MORPHO_CUDA_DRYHOOKS") && atoi(getenv("MORPHO_CUDA_DRYHOOKS")) != 0)) return;
+        mc_dry = true;
     }
     int nhooks = 0;
     /* (1) generic pass: flush device-resident arguments before any builtin that is not accelerated */
     const char *rmin = getenv("MORPHO_CUDA_RESIDENT_MIN");
     if (rmin) mc_resident_min = atol(rmin);
-    bool resident = mc_resident_min >= 0 && !mc_paranoid;
+    bool resident = mc_resident_min >= 0 && !mc_paranoid && !mc_dry;
     if (!resident) mc_resident_min = 0x7fffffffffffL;
     if (resident) nhooks += hook_everything();
     /* (2) writers: what they invalidate */
@@ -965,11 +973,21 @@ void morphocuda_initialize(void) {
     defn = object_getdefn(&probe);
     if (resident && defn && defn->freefn != mc_matrixfree) { orig_matrixfree = defn->freefn; defn->freefn = mc_matrixfree; }
 
-    mc_ready = true;
+    pairwise_initialize();
+    mc_ready = !mc_dry;
     if (mc_verbose) fprintf(stderr, "[morphocuda] ready: %d builtins re-pointed, %d writers hooked\n", npatched, nhooks);
 }
 
+void morphocuda_initialize(void) {
+    /* the script-visible helpers go into the table of the extension being imported (extensions.c:140-156) */
+    builtin_addfunction("cudastats", mc_stats, MORPHO_FN_ALLOCATES);
+    builtin_addfunction("cudatranslate", mc_translate_fn, MORPHO_FN_ALLOCATES);
+    mc_core_initialize();
+}
+
 void morphocuda_finalize(void) {
+    if (!mc_core_done) return;
+    mc_core_done = false;
     mc_ready = false;
     while (nshadows > 0) shadow_drop(&shadows[nshadows - 1]);
     while (nmirrors > 0) mirror_drop(nmirrors - 1);

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+# usage: gpurun_retry.sh <log> <gpurun args...> : retry while the pod answers busy (exit 3)
+log=$1; shift
+for i in $(seq 1 20); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1; rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 120
+done
+exit 3

@@ -58,6 +58,23 @@ def test_extension_loads_and_is_inert_without_a_gpu(tmp_path):
     assert ref == new[:-1]
 
 
+def test_pairwise_patch_hands_over_to_the_module_without_a_gpu(tmp_path):
+    """Host logic of morpho_b200/ext/mc_pairwise.h on a machine without a GPU (MORPHO_CUDA_DRYHOOKS=1 installs the
+    trampolines and the class patch although nothing can be accelerated): the compiled PairwisePotential class of
+    modules/functionals.morpho is found and patched, its subclass too, and every call is handed to the saved script
+    method — the output is the stock reference's, character for character."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    src = script("pairwise.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho",
+                   {"MORPHO_CUDA_VERBOSE": "1", "MORPHO_CUDA_DRYHOOKS": "1"})
+    assert "PairwisePotential patched" in err, err
+    assert [int(x) for x in NUM.findall(new[-1])] == [0, 0, 0, 24, 0, 0, 0, 0, 0, 0], new[-1]     # 8 potentials x 3 methods
+    assert ref == new[:-1]
+
+
 def _run_program(prog, x, q):
     """The postfix machine of include/morpho_cuda.h (mcu_expr_op), in Python."""
     import math
@@ -215,6 +232,59 @@ def test_catenoid_example_as_shipped(tmp_path):
     print(f"catenoid as shipped: {len(hr) - 1} iterations, final energy {hn[-1]:.12g}, worst per-iteration relative difference {worst:.2e}")
     assert worst <= 1e-12, worst
     compare(ref[:i], new[:i], 1e-5)                                # the report lines print 6 significant digits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident_min", [None, "1"])
+def test_pairwise_potential_behind_the_script_api(tmp_path, resident_min):
+    """modules/functionals.morpho imported AS SHIPPED; the extension patches the compiled
+    PairwisePotential class in place (morpho_b200/ext/mc_pairwise.h) so that integrand / gradient / total run as the
+    all-pairs kernel.  Coulomb in two spellings, Lennard-Jones with a cutoff, a power law (Laurent family, recognised from
+    the closures' bytecode), Yukawa and a func/grad pair that do not match (run as programs), a subclass; closures with
+    control flow stay on the module's interpreted loop (3 calls).  Every printed number agrees with the stock run."""
+    src = script("pairwise.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    env = {"MORPHO_CUDA_VERBOSE": "1"}
+    if resident_min:
+        env["MORPHO_CUDA_RESIDENT_MIN"] = resident_min          # results stay on the device as shadowed matrices
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", env)
+    assert "ready:" in err and "PairwisePotential patched" in err, err
+    stats = [float(x) for x in NUM.findall(new[-1])]
+    evals, fallbacks = stats[0], stats[3]
+    assert evals == 7 * 3 and fallbacks == 3, (stats, err)
+    compare(ref, new[:-1], 1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="oracle/_ref/examples not built")
+def test_thomson_example_as_shipped(tmp_path):
+    """BASELINE.json config 3's script: examples/thomson/thomson.morpho (PairwisePotential Coulomb + ScalarPotential level
+    set, ShapeOptimizer.relax(5) + conjugategradient(1000)).  The builtin random() is seeded from the clock, so a seeded
+    script-level `fn random()` is put in front (otherwise no two runs of the STOCK reference agree either) and the
+    viewer block at the end is dropped; nothing else is touched.  Stock reference against `import morphocuda`: same
+    number of iterations; the energy after each of the first 50 iterations equal to 1e-10 relative (every iteration
+    amplifies round-off: 100 mutually repelling charges), the final energy to 1e-8."""
+    text = open(os.path.join(EXAMPLES, "thomson", "thomson.morpho")).read()
+    text = text[:text.index("// Visualize the results")].replace("import plot\n", "")
+    assert "PairwisePotential(fn (r) 1/r, fn (r) -1/r^2)" in text and "conjugategradient(1000)" in text
+    pre = "var _seed = 12345.0\nfn random() { _seed = mod(_seed*16807.0, 2147483647.0); return _seed/2147483647.0 }\n"
+    tail = 'print "history ${opt.energy.count()}"\nfor (e in opt.energy) print e.format("%.17g")\n'
+    src = pre + text + tail
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    assert "PairwisePotential patched" in err, err
+    stats = [float(x) for x in NUM.findall(new[-1])]
+    assert stats[0] > 100 and stats[3] == 0, stats                 # evaluations on the GPU, none left to the reference
+    i = ref.index([l for l in ref if l.startswith("history")][0])
+    hr, hn = [float(x) for x in ref[i + 1:]], [float(x) for x in new[i + 1:-1]]
+    worst50 = max(abs(a - b) / abs(a) for a, b in zip(hr[:50], hn[:50]))
+    from tests.parity import record
+    record("extension", "thomson_as_shipped.energy_history_first50", worst50)
+    record("extension", "thomson_as_shipped.final_energy", abs(hr[-1] - hn[-1]) / abs(hr[-1]))
+    print(f"thomson as shipped: {len(hr)} / {len(hn)} energies, worst of the first 50: {worst50:.2e}, final {hr[-1]:.15g} vs {hn[-1]:.15g}")
+    assert worst50 <= 1e-10, worst50
+    assert abs(hr[-1] - hn[-1]) <= 1e-8 * abs(hr[-1])
+    assert abs(len(hr) - len(hn)) <= 5, (len(hr), len(hn))
 
 
 @pytest.mark.gpu
