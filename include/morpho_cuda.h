@@ -57,7 +57,8 @@ enum {
     MCU_F_GRADSQ = 7,          /* functional.c:3485-3732 */
     MCU_F_NORMSQ = 8,          /* functional.c:4149-4194 */
     MCU_F_NEMATIC = 9,         /* functional.c:3750-3984 */
-    MCU_F_NEMATICELECTRIC = 10 /* functional.c:3996-4142 */
+    MCU_F_NEMATICELECTRIC = 10,/* functional.c:3996-4142 */
+    MCU_F_EQUIELEMENT = 11     /* functional.c:2775-2922 */
 };
 
 /* ---- evaluation modes = the builtin method names (functional.h:55-60) ---- */
@@ -91,6 +92,11 @@ typedef struct mcu_functional {
     int integrandonly;   /* LineCurvatureSq (functional.c:2956-2958)                   */
     mcu_field *field[2]; /* [0] director / q ; [1] electric potential (scalar)         */
     int wrt;             /* MCU_FIELDGRADIENT: which of field[] is differentiated      */
+    /* EquiElement (equielementref, functional.c:2766-2772): `grade` above is the grade of the elements whose sizes are
+     * compared (< 0 or > max grade: the highest grade present); weights are one double per element of that grade in
+     * HOST memory (the 1 x nel Matrix of the `weight` option), NULL / 0 for the unweighted functional */
+    const double *host_weight;
+    int nweight;
 } mcu_functional;
 
 /* ---- library lifetime (replaces nothing: extension _initialize/_finalize, extensions.c:134-154) ---- */

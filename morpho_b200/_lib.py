@@ -19,7 +19,7 @@ MCU_PW_COULOMB, MCU_PW_LAURENT, MCU_PW_YUKAWA, MCU_PW_PROGRAM = range(4)
 
 FUNCTIONAL_IDS = {
     "Length": 1, "AreaEnclosed": 2, "Area": 3, "VolumeEnclosed": 4, "Volume": 5,
-    "LineCurvatureSq": 6, "GradSq": 7, "NormSq": 8, "Nematic": 9, "NematicElectric": 10,
+    "LineCurvatureSq": 6, "GradSq": 7, "NormSq": 8, "Nematic": 9, "NematicElectric": 10, "EquiElement": 11,
 }
 
 
@@ -27,7 +27,8 @@ class McuFunctional(C.Structure):
     _fields_ = [("functional", C.c_int), ("grade", C.c_int),
                 ("ksplay", C.c_double), ("ktwist", C.c_double), ("kbend", C.c_double), ("pitch", C.c_double),
                 ("haspitch", C.c_int), ("integrandonly", C.c_int),
-                ("field", C.c_void_p * 2), ("wrt", C.c_int)]
+                ("field", C.c_void_p * 2), ("wrt", C.c_int),
+                ("host_weight", C.c_void_p), ("nweight", C.c_int)]
 
 
 class MorphoError(RuntimeError):

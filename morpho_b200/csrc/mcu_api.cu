@@ -425,7 +425,7 @@ static int functional_grade(const mcu_mesh *m, const mcu_functional *f) {
         case MCU_F_LENGTH: case MCU_F_AREAENCLOSED: return 1;
         case MCU_F_AREA: case MCU_F_VOLUMEENCLOSED: return 2;
         case MCU_F_VOLUME: return 3;
-        case MCU_F_LINECURVATURESQ: case MCU_F_NORMSQ: return 0;
+        case MCU_F_LINECURVATURESQ: case MCU_F_NORMSQ: case MCU_F_EQUIELEMENT: return 0;
         case MCU_F_GRADSQ: case MCU_F_NEMATIC: case MCU_F_NEMATICELECTRIC:
             return f->grade > 0 ? f->grade : mesh_maxgrade(m);  // gradsq_prepareref, functional.c:3622-3642
     }
@@ -531,6 +531,25 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
         if (rc) return rc;
         v.lrix = m->conn[1].d_rix; v.ltptr = m->conn[1].d_tptr; v.ltidx = m->conn[1].d_tidx;
     }
+    double *d_weight = nullptr;
+    if (F == MCU_F_EQUIELEMENT) {
+        // equielement_prepareref (functional.c:2775-2806): a grade outside 0..maxgrade means the highest grade present
+        const int maxg = mesh_maxgrade(m);
+        const int eg = (f->grade < 0 || f->grade > maxg) ? maxg : f->grade;
+        if (eg < 1 || !m->conn[eg].present) { mcu_set_error("EquiElement needs elements of grade >= 1"); return MCU_ERR_UNSUPPORTED; }
+        int rc = mcu_ensure_transpose(m, eg);
+        if (rc) return rc;
+        p.egrade = eg;
+        v.lrix = m->conn[eg].d_rix; v.ltptr = m->conn[eg].d_tptr; v.ltidx = m->conn[eg].d_tidx;
+        if (f->host_weight && f->nweight > 0) {
+            double sum = 0.0, cc = 0.0;                       // matrix_sum (matrix.c:591-603) / ncols
+            for (int i = 0; i < f->nweight; i++) { double y = f->host_weight[i] - cc, t = sum + y; cc = (t - sum) - y; sum = t; }
+            p.wmean = sum / f->nweight; p.nweight = f->nweight;
+            CK(cudaMallocAsync((void **) &d_weight, sizeof(double) * (size_t) f->nweight, g_stream));
+            CK(cudaMemcpyAsync(d_weight, f->host_weight, sizeof(double) * (size_t) f->nweight, cudaMemcpyHostToDevice, g_stream));
+            v.weight = d_weight;
+        }
+    }
     const bool gather = (mode == MCU_GRADIENT || mode == MCU_FIELDGRADIENT) && g > 0;
     if (gather && !sel) {
         int rc = mcu_ensure_transpose(m, g);
@@ -582,6 +601,7 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
         default:
             return MCU_ERR_ARGS;
     }
+    if (d_weight) cudaFreeAsync(d_weight, g_stream);
     if (e != cudaSuccess) { mcu_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return MCU_ERR_CUDA; }
     return MCU_OK;
 }

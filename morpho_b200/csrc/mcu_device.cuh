@@ -32,6 +32,9 @@ struct McuParams {
     double ksplay, ktwist, kbend, pitch;
     int haspitch, integrandonly;
     int wrt;
+    int egrade;       // EquiElement: grade of the elements whose sizes are compared
+    int nweight;      // EquiElement: number of weights (0: unweighted)
+    double wmean;     // EquiElement: mean weight (equielement_prepareref, functional.c:2797-2803)
 };
 
 struct McuView {
@@ -44,11 +47,12 @@ struct McuView {
     // vertex → compact element incidence (CSR transpose), element ids ascending per vertex
     const int *tptr;
     const int *tidx;
-    // LineCurvatureSq: line elements and their transpose
+    // LineCurvatureSq: line elements and their transpose; EquiElement: the elements of grade egrade and their transpose
     const int *lrix;
     const int *ltptr;
     const int *ltidx;
     const unsigned char *selmask;  // grade-0 selections: 1 where the vertex element is selected
+    const double *weight;          // EquiElement: one weight per element, or nullptr
     unsigned *flags;               // device status word (MCU_FLAG_*)
 };
 

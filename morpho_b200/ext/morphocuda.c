@@ -84,9 +84,11 @@ static mc_mirror *mirror_find(objectmesh *mesh) {
     return NULL;
 }
 
+static void field_mark_range(const double *elements);
 static void mirror_mark_matrix(objectmatrix *a) {
     for (int i = 0; i < nmirrors; i++)
         if (mirrors[i].vert == a || mirrors[i].elements == a->elements) mirrors[i].vert_dirty = true;
+    field_mark_range(a->elements);
 }
 
 /* a device-resident Matrix is going away (mc_resident.h shadow_drop): mirrors reading from it return to their own buffer */
@@ -162,11 +164,13 @@ static mc_mirror *mirror_get(objectmesh *mesh, grade g) {
 /* ------------------------------------------------------------------ field mirrors */
 
 /* Vertex (P1) fields only: one entry per vertex, psize doubles each, no finite-element space (field.c:419-434).
- * The device copy is refreshed on EVERY evaluation: fields are written through pool Matrix objects that alias the
- * store (field.c:309-327, 1128-1132), which the vertex-matrix hooks do not cover yet; the upload is small next to the
- * finite-difference kernels it feeds. */
+ * The device copy is refreshed only when the VM wrote to the Field: its own writers (Field.setindex / assign / acc,
+ * field.c:1136-1144) are wrapped, and writes through the Matrix objects that ALIAS its store — the pool matrices
+ * Field_getindex hands out (field.c:309-327) and the store itself from __linearize (field.c:1128-1132) — are caught
+ * by address range in the Matrix writer hooks (field_mark_range).  A Field that dies takes its mirrors with it.
+ * MORPHO_CUDA_PARANOID=1 uploads on every evaluation instead. */
 #define MC_MAXFIELDS 32
-typedef struct { objectfield *fld; mcu_mesh *m; mcu_field *f; int psize, nv; long used; } mc_fieldmirror;
+typedef struct { objectfield *fld; mcu_mesh *m; mcu_field *f; int psize, nv; long used; double *elements; bool dirty; } mc_fieldmirror;
 static mc_fieldmirror fields[MC_MAXFIELDS];
 static int nfields = 0;
 static long mc_stat_field_uploads = 0;
@@ -184,6 +188,23 @@ static bool field_is_vertex_field(objectfield *fld, objectmesh *mesh) {
     for (unsigned int g = 1; g < fld->ngrades; g++) if (fld->dof[g] != 0) return false;
     if (fld->psize < 1 || fld->psize > 9) return false;
     return fld->data.nels == (MatrixCount_t) mesh->vert->ncols * fld->psize;
+}
+
+static void field_mark(objectfield *fld) {
+    for (int i = 0; i < nfields; i++) if (fields[i].fld == fld) fields[i].dirty = true;
+}
+
+/* a Matrix at `elements` was written: it may alias the store of a mirrored Field */
+static void field_mark_range(const double *elements) {
+    for (int i = 0; i < nfields; i++)
+        if (elements >= fields[i].elements && elements < fields[i].elements + (size_t) fields[i].nv * fields[i].psize) fields[i].dirty = true;
+}
+
+static void fields_drop_field(objectfield *fld) {
+    for (int i = 0; i < nfields;) {
+        if (fields[i].fld == fld) { mcu_field_destroy(fields[i].f); fields[i] = fields[--nfields]; }
+        else i++;
+    }
 }
 
 static mcu_field *field_get(objectfield *fld, mc_mirror *mr) {
@@ -205,11 +226,18 @@ static mcu_field *field_get(objectfield *fld, mc_mirror *mr) {
         fm->f = mcu_field_create(mr->m, (int) fld->psize);
         if (!fm->f) return NULL;
         fm->fld = fld; fm->m = mr->m; fm->psize = (int) fld->psize; fm->nv = mr->nv;
+        fm->elements = NULL; fm->dirty = true;
         nfields++;
     }
     fm->used = mc_call_gen;
-    if (mcu_field_set(fm->f, fld->data.elements) != MCU_OK) return NULL;
-    mc_stat_field_uploads++;
+    /* the store handed out by __linearize may have become a device-resident Matrix that was written there */
+    mc_shadow *fs = nshadows > 0 ? shadow_find(&fld->data) : NULL;
+    if (fs && !fs->host_valid) { if (!shadow_to_host(fs)) return NULL; fm->dirty = true; }
+    if (fm->dirty || fm->elements != fld->data.elements || mc_paranoid) {
+        if (mcu_field_set(fm->f, fld->data.elements) != MCU_OK) return NULL;
+        fm->elements = fld->data.elements; fm->dirty = false;
+        mc_stat_field_uploads++;
+    }
     return fm->f;
 }
 
@@ -454,6 +482,75 @@ MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, total, MCU_TOTAL)
 MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, integrand, MCU_INTEGRAND)
 MC_PVENEER(LineCurvatureSq, MCU_F_LINECURVATURESQ, gradient, MCU_GRADIENT)
 
+/* EquiElement total / integrand / gradient (functional.c:2775-2922; the regulariser of examples/tactoid/tactoid.morpho:16).
+ * Properties: grade (-1: highest grade of the mesh) and weight (a 1 x nel Matrix or nil).  Failures of the map
+ * (a vertex whose elements have zero mean size raises EquiElArgs in the reference) go to the reference builtin. */
+static bool mc_eval_equielement(vm *v, int nargs, value *args, int mode, value *out) {
+    functional_mapinfo info;
+    *out = MORPHO_NIL;
+    if (!mc_ready || !MORPHO_ISINSTANCE(MORPHO_SELF(args))) return false;
+    if (!functional_validateargs(v, nargs, args, &info)) return true;
+    objectinstance *self = MORPHO_GETINSTANCE(MORPHO_SELF(args));
+    if (info.field || (info.sel && info.sel->mode != SELECT_SOME)) return false;
+    value val = MORPHO_NIL;
+    if (!prop(self, FUNCTIONAL_GRADE_PROPERTY, &val) || !MORPHO_ISINTEGER(val)) return false;       /* equielement_prepareref fails: EquiElArgs */
+    int eg = MORPHO_GETINTEGERVALUE(val), maxg = (int) mesh_maxgrade(info.mesh);
+    if (eg < 0 || eg > maxg) eg = maxg;
+    if (eg < 1 || eg > 3 || mesh_has_symmetries(info.mesh, eg)) return false;
+    /* the reference leaves conn(grade, 0) behind in the mesh (mesh_addconnectivityelement, functional.c:2791): so do we */
+    if (!mesh_addconnectivityelement(info.mesh, eg, 0) || !mesh_getconnectivityelement(info.mesh, 0, eg)) return false;
+    mcu_functional f;
+    memset(&f, 0, sizeof(f));
+    f.functional = MCU_F_EQUIELEMENT; f.grade = eg;
+    if (prop(self, EQUIELEMENT_WEIGHT_PROPERTY, &val) && MORPHO_ISMATRIX(val)) {
+        objectmatrix *w = MORPHO_GETMATRIX(val);
+        if (w->nvals != 1 || w->nrows != 1) return false;          /* matrix_getelement(weight, 0, el): a row of weights */
+        if (!shadow_to_host(shadow_find(w))) return false;
+        f.host_weight = w->elements; f.nweight = (int) w->ncols;
+    }
+    mc_mirror *mr = mirror_get(info.mesh, eg);
+    if (!mr) return false;
+    mcu_selection *sel = NULL;
+    if (info.sel) {
+        int *ids, n = selection_ids(info.sel, 0, &ids);
+        if (n < 0) return false;
+        sel = mcu_selection_create(mr->m, 0, n, ids);
+        free(ids);
+        if (!sel) return false;
+    }
+    int rc = MCU_OK;
+    objectmatrix *new = NULL;
+    double total = 0.0;
+    switch (mode) {
+        case MCU_TOTAL: rc = mcu_eval(mr->m, &f, sel, MCU_TOTAL, &total); break;
+        case MCU_INTEGRAND: rc = eval_matrix_result(mr, &f, sel, MCU_INTEGRAND, 1, mr->nv, &new); break;
+        case MCU_GRADIENT: rc = eval_matrix_result(mr, &f, sel, MCU_GRADIENT, mr->dim, mr->nv, &new); break;
+        default: rc = MCU_ERR_UNSUPPORTED;
+    }
+    if (sel) mcu_selection_destroy(sel);
+    if (rc == MCU_OK) {
+        mc_stat_evals++;
+        if (mode == MCU_TOTAL) *out = MORPHO_FLOAT(total);
+        else { *out = MORPHO_OBJECT(new); morpho_bindobjects(v, 1, out); }
+        return true;
+    }
+    if (new) object_free((object *) new);
+    if (rc == -1) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); return true; }
+    mc_log("EquiElement not accelerated:", mcu_last_error());
+    return false;
+}
+#define MC_EVENEER(meth, MODE) \
+    static builtinfunction orig_EquiElement_##meth = NULL; \
+    static value mc_EquiElement_##meth(vm *v, int nargs, value *args) { \
+        value out; \
+        if (mc_eval_equielement(v, nargs, args, MODE, &out)) return out; \
+        mc_stat_fallbacks++; \
+        return orig_EquiElement_##meth(v, nargs, args); \
+    }
+MC_EVENEER(total, MCU_TOTAL)
+MC_EVENEER(integrand, MCU_INTEGRAND)
+MC_EVENEER(gradient, MCU_GRADIENT)
+
 /* LineIntegral / AreaIntegral, total and integrand (functional.c:5186-5243, 5371-5426).  The integrand closure is
  * translated into a postfix program (mc_translate.h); what cannot be translated — and method dictionaries, reference
  * meshes, fields on finite-element spaces — goes to the reference builtin. */
@@ -664,7 +761,7 @@ MC_VENEER(AreaEnclosed, MCU_F_AREAENCLOSED, MESH_GRADE_LINE, integrand, MCU_INTE
  *           newest copy is on the device are brought to the host;
  *   post    what the builtin wrote: the receiver Matrix (its device copy and the mirrors reading it are stale), a
  *           mesh's vertices, connectivity. */
-typedef enum { WRAP_NONE, WRAP_MATRIX_SELF, WRAP_MATRIX_RESHAPE, WRAP_MESH_VERTS, WRAP_MESH_CONN, WRAP_CONN_ALL } mc_wrapkind;
+typedef enum { WRAP_NONE, WRAP_MATRIX_SELF, WRAP_MATRIX_RESHAPE, WRAP_MESH_VERTS, WRAP_MESH_CONN, WRAP_CONN_ALL, WRAP_FIELD_SELF } mc_wrapkind;
 static struct { builtinfunction orig; mc_wrapkind kind; mc_accel accel; bool flush; } wraps[MC_MAXWRAPS];
 static int nwraps = 0;
 
@@ -677,9 +774,11 @@ static value wrap_call(int slot, vm *v, int nargs, value *args) {
     mc_wrapkind kind = wraps[slot].kind;
     objectmatrix *mat = ((kind == WRAP_MATRIX_SELF || kind == WRAP_MATRIX_RESHAPE) && MORPHO_ISMATRIX(self)) ? MORPHO_GETMATRIX(self) : NULL;
     objectmesh *mesh = ((kind == WRAP_MESH_VERTS || kind == WRAP_MESH_CONN) && MORPHO_ISMESH(self)) ? MORPHO_GETMESH(self) : NULL;
+    objectfield *fld = (kind == WRAP_FIELD_SELF && MORPHO_ISFIELD(self)) ? MORPHO_GETFIELD(self) : NULL;
     r = wraps[slot].orig(v, nargs, args);
     switch (kind) {
         case WRAP_NONE: break;
+        case WRAP_FIELD_SELF: if (fld) field_mark(fld); break;
         case WRAP_MATRIX_SELF: case WRAP_MATRIX_RESHAPE:
             if (mat) {
                 mirror_mark_matrix(mat);
@@ -822,6 +921,13 @@ static void mc_meshfree(object *obj) {
     if (orig_meshfree) orig_meshfree(obj);
 }
 
+/* Field objects that die take their device mirrors with them (a later Field may be allocated at the same address) */
+static objectfreefn orig_fieldfree = NULL;
+static void mc_fieldfree(object *obj) {
+    if (nfields > 0) fields_drop_field((objectfield *) obj);
+    if (orig_fieldfree) orig_fieldfree(obj);
+}
+
 /* Matrix objects that die take their device shadow with them (objectmatrixdefn.freefn is NULL in the reference) */
 static objectfreefn orig_matrixfree = NULL;
 static void mc_matrixfree(object *obj) {
@@ -925,6 +1031,9 @@ static void mc_core_initialize(void) {
     nhooks += hook_writers("Mesh", MESH_REMOVEGRADE_METHOD, WRAP_MESH_CONN);
     nhooks += hook_writers("Mesh", MESH_RESETCONNECTIVITY_METHOD, WRAP_MESH_CONN);
     nhooks += hook_writers("Mesh", MESH_ADDSYMMETRY_METHOD, WRAP_MESH_CONN);
+    nhooks += hook_writers("Field", MORPHO_SETINDEX_METHOD, WRAP_FIELD_SELF);
+    nhooks += hook_writers("Field", MORPHO_ASSIGN_METHOD, WRAP_FIELD_SELF);
+    nhooks += hook_writers("Field", MORPHO_ACC_METHOD, WRAP_FIELD_SELF);
     nhooks += hook_writers("Sparse", SPARSE_SETROWINDICES_METHOD, WRAP_CONN_ALL);
     nhooks += hook_writers("Sparse", MORPHO_SETINDEX_METHOD, WRAP_CONN_ALL);
     /* (3) the Matrix methods of optimize.morpho's line searches, on device-resident matrices (mc_resident.h) */
@@ -960,6 +1069,7 @@ static void mc_core_initialize(void) {
     PATCH(Nematic, total); PATCH(Nematic, integrand); PATCH(Nematic, gradient); PATCH(Nematic, fieldgradient);
     PATCH(NematicElectric, total); PATCH(NematicElectric, integrand); PATCH(NematicElectric, gradient); PATCH(NematicElectric, fieldgradient);
     PATCH(LineCurvatureSq, total); PATCH(LineCurvatureSq, integrand); PATCH(LineCurvatureSq, gradient);
+    PATCH(EquiElement, total); PATCH(EquiElement, integrand); PATCH(EquiElement, gradient);
     PATCH(ScalarPotential, total); PATCH(ScalarPotential, integrand); PATCH(ScalarPotential, gradient);
     PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
     PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
@@ -969,6 +1079,9 @@ static void mc_core_initialize(void) {
     probe.type = OBJECT_MESH;
     objecttypedefn *defn = object_getdefn(&probe);
     if (defn && defn->freefn != mc_meshfree) { orig_meshfree = defn->freefn; defn->freefn = mc_meshfree; }
+    probe.type = OBJECT_FIELD;
+    defn = object_getdefn(&probe);
+    if (defn && defn->freefn != mc_fieldfree) { orig_fieldfree = defn->freefn; defn->freefn = mc_fieldfree; }
     probe.type = OBJECT_MATRIX;
     defn = object_getdefn(&probe);
     if (resident && defn && defn->freefn != mc_matrixfree) { orig_matrixfree = defn->freefn; defn->freefn = mc_matrixfree; }

@@ -19,7 +19,7 @@ from ._lib import (MCU_FIELDGRADIENT, MCU_GRADIENT, MCU_INTEGRAND, MCU_TOTAL, FU
                    MorphoError, check, lib)
 from .geometry import Field, Mesh, Selection
 
-__all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq",
+__all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq", "EquiElement",
            "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral", "ScalarPotential"]
 
 
@@ -45,6 +45,10 @@ class Functional:
         for i, f in enumerate(self.fields[:2]):
             d.field[i] = f._h
         d.wrt = wrt
+        w = getattr(self, "weight", None)
+        if w is not None:
+            self._w = np.ascontiguousarray(w, dtype=np.float64).ravel()      # kept alive for the call
+            d.host_weight, d.nweight = self._w.ctypes.data, self._w.size
         return d
 
     @staticmethod
@@ -68,7 +72,7 @@ class Functional:
             g = int(getattr(self, "grade", -1) or -1)
             return g if g > 0 else mesh.maxgrade()
         return {"Length": 1, "AreaEnclosed": 1, "Area": 2, "VolumeEnclosed": 2, "Volume": 3,
-                "LineCurvatureSq": 0, "NormSq": 0}[self.name]
+                "LineCurvatureSq": 0, "NormSq": 0, "EquiElement": 0}[self.name]
 
     def _eval(self, mode, args, wrt=0):
         mesh, sel, fld = self._args(args)
@@ -120,6 +124,22 @@ class VolumeEnclosed(Functional):
 
 class Volume(Functional):
     name = "Volume"
+
+
+class EquiElement(Functional):
+    """EquiElement(grade=-1, weight=None) (functional.c:2775-2922): per vertex, the variance of the sizes of the incident
+    elements of ``grade`` (default: the highest grade of the mesh) relative to their mean; ``weight``: one number per
+    element (the reference's 1 x nel Matrix).  Gradient by the reference's central differences."""
+    name = "EquiElement"
+
+    def __init__(self, grade=-1, weight=None):
+        super().__init__()
+        self.grade, self.weight = grade, weight
+
+    def _desc(self, wrt=0):
+        d = super()._desc(wrt)
+        d.grade = int(self.grade)          # 0 is a legal value here (it means "the highest grade", like -1)
+        return d
 
 
 class LineCurvatureSq(Functional):

@@ -104,6 +104,9 @@ typedef struct {
     int g;               /* grade looped over */
     /* LineCurvatureSq: conn(1,0) transpose of the line elements */
     int *ltptr, *ltidx;
+    /* EquiElement: grade of the elements compared, conn(grade,0) transpose, mean weight */
+    int eg, *etptr, *etidx;
+    double wmean;
 } ctx;
 
 static const double *X(const ctx *c, int v) { return c->vert + (size_t) v * c->m->dim; }
@@ -315,7 +318,9 @@ static int nematicelectric_integrand(const ctx *c, int nv, const int *vid, doubl
     for (int i = 0; i < nv; i++) nn[i] = f->field[0] + (size_t) vid[i] * psize;
     if (c->g == 2) { if (!evaluategradient(c, f->field[1], f->psize[1], nv, vid, ee)) return 0; }
     else if (c->g == 3) { if (!evaluategradient3d(c, f->field[1], f->psize[1], nv, vid, ee)) return 0; }
-    double nnt[3][MO_MAXNV];
+    /* in 2D the reference reads ee[2] and nnt[2] past the end of its dim-sized arrays (functional.c:4067, 4077-4087);
+     * the golden outputs record the value those terms had there: zero */
+    double nnt[3][MO_MAXNV] = {{0}};
     for (int i = 0; i < nv; i++) for (int j = 0; j < dim; j++) nnt[j][i] = nn[i][j];
     double total = ee[0] * ee[0] * bcintfg(nv, nnt[0], nnt[0]) +
                    ee[1] * ee[1] * bcintfg(nv, nnt[1], nnt[1]) +
@@ -327,8 +332,40 @@ static int nematicelectric_integrand(const ctx *c, int nv, const int *vid, doubl
     return 1;
 }
 
+/* equielement_integrand (functional.c:2847-2893): the element is a vertex; the sizes of the elements of grade eg
+ * incident to it (conn(eg,0), ascending element id) are compared with their mean */
+static int equielement_integrand(const ctx *c, int id, double *out) {
+    int nconn = c->etptr[id + 1] - c->etptr[id];
+    const int *conn = c->etidx + c->etptr[id];
+    if (nconn == 1) { *out = 0; return 1; }
+    double *size = malloc(sizeof(double) * (size_t) (nconn > 0 ? nconn : 1)), mean = 0.0, total = 0.0;
+    for (int i = 0; i < nconn; i++) {
+        elementsize(c, c->eg, c->eg + 1, c->m->conn[c->eg] + (size_t) conn[i] * (c->eg + 1), &size[i]);
+        mean += size[i];
+    }
+    mean /= ((double) nconn);
+    if (fabs(mean) < MO_EPS) { free(size); return 0; }
+    if (!c->f->weight || fabs(c->wmean) < MO_EPS) {
+        for (int i = 0; i < nconn; i++) total += (1.0 - size[i] / mean) * (1.0 - size[i] / mean);
+    } else {
+        double wmean = 0.0;
+        for (int i = 0; i < nconn; i++) wmean += (conn[i] < c->f->nweight ? c->f->weight[conn[i]] : 1.0);   /* matrix_getelement out of bounds leaves 1.0 */
+        wmean /= ((double) nconn);
+        if (fabs(wmean) < MO_EPS) wmean = 1.0;
+        for (int i = 0; i < nconn; i++) {
+            double w = (conn[i] < c->f->nweight ? c->f->weight[conn[i]] : 1.0);
+            double term = (1.0 - w * size[i] / mean / wmean);
+            total += term * term;
+        }
+    }
+    free(size);
+    *out = total;
+    return 1;
+}
+
 static int integrand(const ctx *c, int id, int nv, const int *vid, double *out) {
     switch (c->f->functional) {
+        case MO_EQUIELEMENT: return equielement_integrand(c, id, out);
         case MO_LENGTH: return length_integrand(c, nv, vid, out);
         case MO_AREAENCLOSED: return areaenclosed_integrand(c, nv, vid, out);
         case MO_AREA: return area_integrand(c, nv, vid, out);
@@ -425,7 +462,7 @@ int mo_default_grade(const mo_mesh *m, const mo_functional *f) {
         case MO_LENGTH: case MO_AREAENCLOSED: return 1;
         case MO_AREA: case MO_VOLUMEENCLOSED: return 2;
         case MO_VOLUME: return 3;
-        case MO_LINECURVATURESQ: case MO_NORMSQ: return 0;
+        case MO_LINECURVATURESQ: case MO_NORMSQ: case MO_EQUIELEMENT: return 0;
         case MO_GRADSQ: case MO_NEMATIC: case MO_NEMATICELECTRIC:
             return (f->grade > 0 ? f->grade : maxg); /* gradsq_prepareref, functional.c:3622-3642 */
     }
@@ -459,10 +496,25 @@ static int ctx_init(ctx *c, const mo_mesh *m, const mo_functional *f) {
         c->ltidx = malloc(sizeof(int) * (size_t) m->nel[1] * 2 + 1);
         mo_transpose(m->nv, m->nel[1], 2, m->conn[1], c->ltptr, c->ltidx);
     }
+    if (f->functional == MO_EQUIELEMENT) {
+        /* equielement_prepareref (functional.c:2775-2806): grade outside 0..maxgrade means the highest grade present */
+        int maxg = 0;
+        for (int g = m->dim; g > 0; g--) if (m->conn[g] && m->nel[g] > 0) { maxg = g; break; }
+        c->eg = (f->grade < 0 || f->grade > maxg) ? maxg : f->grade;
+        if (c->eg < 1 || !m->conn[c->eg]) { free(c->vert); return MO_ERR_ARGS; }
+        c->etptr = malloc(sizeof(int) * (size_t) (m->nv + 1));
+        c->etidx = malloc(sizeof(int) * ((size_t) m->nel[c->eg] * (c->eg + 1) + 1));
+        mo_transpose(m->nv, m->nel[c->eg], c->eg + 1, m->conn[c->eg], c->etptr, c->etidx);
+        if (f->weight && f->nweight > 0) {       /* matrix_sum / ncols */
+            double sum = 0.0, cc = 0.0;
+            for (int i = 0; i < f->nweight; i++) { double y = f->weight[i] - cc, t = sum + y; cc = (t - sum) - y; sum = t; }
+            c->wmean = sum / f->nweight;
+        }
+    }
     return MO_OK;
 }
 
-static void ctx_free(ctx *c) { free(c->vert); free(c->ltptr); free(c->ltidx); }
+static void ctx_free(ctx *c) { free(c->vert); free(c->ltptr); free(c->ltidx); free(c->etptr); free(c->etidx); }
 
 static void element(const ctx *c, int id, int *nv, const int **vid, int *self) {
     if (c->g == 0) { *self = id; *nv = 1; *vid = self; }
@@ -523,6 +575,20 @@ static int numericalgrad_vertex(ctx *c, int eid, int vtx, int nv, const int *vid
  * vertex of each incident edge in ascending edge id */
 static int dependencies(const ctx *c, int id, int *deps) {
     int n = 0;
+    if (c->f->functional == MO_EQUIELEMENT) {
+        /* equielement_dependencies (functional.c:2817-2844): the other vertices of the incident elements, in order of
+         * discovery, each once; not the vertex itself */
+        for (int q = c->etptr[id]; q < c->etptr[id + 1]; q++) {
+            const int *entries = c->m->conn[c->eg] + (size_t) c->etidx[q] * (c->eg + 1);
+            for (int j = 0; j <= c->eg; j++) {
+                if (entries[j] == id) continue;
+                int seen = 0;
+                for (int k = 0; k < n; k++) if (deps[k] == entries[j]) seen = 1;
+                if (!seen) deps[n++] = entries[j];
+            }
+        }
+        return n;
+    }
     deps[n++] = id;
     for (int q = c->ltptr[id]; q < c->ltptr[id + 1]; q++) {
         const int *entries = c->m->conn[1] + 2 * (size_t) c->ltidx[q];
@@ -542,6 +608,7 @@ int mo_gradient(const mo_mesh *m, const mo_functional *f, const int *sel, int ns
                     f->functional == MO_VOLUMEENCLOSED || f->functional == MO_VOLUME);
     int *deps = NULL;
     if (f->functional == MO_LINECURVATURESQ) deps = malloc(sizeof(int) * (size_t) (2 * m->nel[1] + 2));
+    if (f->functional == MO_EQUIELEMENT) deps = malloc(sizeof(int) * ((size_t) m->nel[c.eg] * (c.eg + 1) + 2));
     for (int k = 0; k < cnt; k++) {
         int i = sel ? sel[k] : k, nv, self, ok = 1; const int *vid;
         element(&c, i, &nv, &vid, &self);

@@ -36,7 +36,8 @@ enum {
     MO_GRADSQ = 7,
     MO_NORMSQ = 8,
     MO_NEMATIC = 9,
-    MO_NEMATICELECTRIC = 10
+    MO_NEMATICELECTRIC = 10,
+    MO_EQUIELEMENT = 11
 };
 
 /* Error codes */
@@ -69,6 +70,9 @@ typedef struct {
     int psize[2];
     double *field[2];     /* nv*psize, vertex-based P1 fields; not const: FD perturbs & restores */
     int wrt;              /* fieldgradient: which field (0/1) to differentiate */
+    /* EquiElement: optional weights, one per element of the grade compared (a 1 x nel Matrix in the reference) */
+    const double *weight;
+    int nweight;
 } mo_functional;
 
 /* functional_fdstepsize (functional.c:46-58) */

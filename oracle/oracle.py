@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 FUNCTIONAL_IDS = {
     "Length": 1, "AreaEnclosed": 2, "Area": 3, "VolumeEnclosed": 4, "Volume": 5,
-    "LineCurvatureSq": 6, "GradSq": 7, "NormSq": 8, "Nematic": 9, "NematicElectric": 10,
+    "LineCurvatureSq": 6, "GradSq": 7, "NormSq": 8, "Nematic": 9, "NematicElectric": 10, "EquiElement": 11,
 }
 
 MO_ERRORS = {1: "args", 2: "FnctlELNtFnd", 3: "degenerate", 4: "VolEnclZero", 5: "unsupported"}
@@ -52,7 +52,8 @@ class _MoFunctional(C.Structure):
     _fields_ = [("functional", C.c_int), ("grade", C.c_int),
                 ("ksplay", C.c_double), ("ktwist", C.c_double), ("kbend", C.c_double), ("pitch", C.c_double),
                 ("haspitch", C.c_int), ("integrandonly", C.c_int),
-                ("psize", C.c_int * 2), ("field", C.POINTER(C.c_double) * 2), ("wrt", C.c_int)]
+                ("psize", C.c_int * 2), ("field", C.POINTER(C.c_double) * 2), ("wrt", C.c_int),
+                ("weight", C.POINTER(C.c_double)), ("nweight", C.c_int)]
 
 
 @dataclass
@@ -67,6 +68,7 @@ class FunctionalSpec:
     pitch: float | None = None
     integrandonly: bool = False
     fields: list = dc_field(default_factory=list)   # list of np.ndarray (nv, psize)
+    weight: object = None                           # EquiElement: one weight per element of the grade compared, or None
 
 
 class Oracle:
@@ -130,6 +132,10 @@ class Oracle:
             f.psize[i] = a.shape[1]
             f.field[i] = _dptr(a)
         f.wrt = wrt
+        if spec.weight is not None:
+            w = np.ascontiguousarray(spec.weight, dtype=np.float64).ravel()
+            keep.append(w)
+            f.weight, f.nweight = _dptr(w), w.size
         return f, keep
 
     def _run(self, fn, vert, grades, spec, sel, nout, wrt=0):
@@ -254,6 +260,7 @@ class Reference:
         L.refh_functional_new.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.c_int,
                                           C.POINTER(C.c_char_p), C.POINTER(C.c_double)]
         L.refh_functional_free.argtypes = [C.c_void_p]
+        L.refh_functional_set_rowmatrix.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
         L.refh_eval.restype = C.c_long
         L.refh_eval.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_double), C.c_long, C.POINTER(C.c_double)]
@@ -376,7 +383,7 @@ class RefMesh:
                 names.append("pitch"); vals.append(spec.pitch)
         if spec.name == "LineCurvatureSq" and spec.integrandonly:
             names.append("integrandonly"); vals.append(1.0)
-        if spec.grade > 0 and spec.name in ("GradSq", "Nematic", "NematicElectric"):
+        if spec.grade > 0 and spec.name in ("GradSq", "Nematic", "NematicElectric", "EquiElement"):
             names.append("grade"); vals.append(float(spec.grade))
         fa = (C.c_void_p * max(len(field_handles), 1))(*field_handles)
         na = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
@@ -384,6 +391,10 @@ class RefMesh:
         h = L.refh_functional_new(spec.name.encode(), len(field_handles), fa, len(names), na, va)
         if not h:
             raise RuntimeError("functional_new failed: " + self.ref.err())
+        if spec.weight is not None:           # EquiElement(weight=Matrix 1 x nel), functional.c:2895-2907
+            w = np.ascontiguousarray(spec.weight, dtype=np.float64).ravel()
+            if L.refh_functional_set_rowmatrix(h, b"weight", w.size, _dptr(w)):
+                raise RuntimeError("functional_set_rowmatrix failed: " + self.ref.err())
         self._funcs.append(h)
         return h
 

@@ -267,6 +267,15 @@ void *refh_functional_new(const char *cls, int nfields, void **fields, int npara
     }
     return inst;
 }
+/* a 1 x n Matrix as a property of the instance (EquiElement's `weight`, functional.c:2895-2907); the matrix is owned by
+ * the harness for the life of the process (a few hundred doubles per golden case) */
+int refh_functional_set_rowmatrix(void *f, const char *name, int n, const double *vals) {
+    objectmatrix *mm = matrix_new(1, n, false);
+    if (!f || !mm) { snprintf(lasterr, sizeof(lasterr), "set_rowmatrix: allocation"); return 1; }
+    memcpy(mm->elements, vals, sizeof(double) * (size_t) n);
+    objectinstance_setproperty((objectinstance *) f, builtin_internsymbolascstring((char *) name), MORPHO_OBJECT(mm));
+    return 0;
+}
 void refh_functional_free(void *f) { if (f) object_free((object *) f); }
 
 /* Evaluate method ∈ {total, integrand, gradient, fieldgradient} of a functional.

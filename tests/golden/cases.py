@@ -34,6 +34,14 @@ def case_sphere(f=4, seed=1):
         evals.append(dict(f=dict(name="Length"), method=method))
         evals.append(dict(f=dict(name="Length"), method=method, sel=(1, sel_edges)))
         evals.append(dict(f=dict(name="AreaEnclosed"), method=method))
+    # appended after the round-1 evaluations so that their fixture keys keep their numbers
+    vsel = np.sort(r.choice(v.shape[0], size=v.shape[0] // 3, replace=False)).astype(np.int32)
+    wts = 0.5 + r.uniform(0, 1, size=c.shape[0])
+    for method in ("total", "integrand", "gradient"):
+        evals.append(dict(f=dict(name="EquiElement"), method=method))
+        evals.append(dict(f=dict(name="EquiElement"), method=method, sel=(0, vsel)))
+        evals.append(dict(f=dict(name="EquiElement", weight=wts), method=method))
+        evals.append(dict(f=dict(name="EquiElement", grade=1), method=method))
     return dict(name=f"sphere_f{f}", vert=v, grades={1: edges, 2: c}, fields={}, evals=evals)
 
 
@@ -95,6 +103,8 @@ def case_disk(n=5, seed=3, dim=3):
     for method in ("total", "integrand", "gradient"):
         evals.append(dict(f=dict(name="Length"), method=method, sel=(1, bsel)))
         evals.append(dict(f=dict(name="Area"), method=method))
+    for method in ("total", "integrand", "gradient"):          # the regulariser of examples/tactoid/tactoid.morpho:16
+        evals.append(dict(f=dict(name="EquiElement"), method=method))
     return dict(name=f"disk_n{n}_d{dim}", vert=v, grades={1: edges, 2: f}, fields=dict(nn=nn, phi=phi, q2=q2), evals=evals)
 
 
