@@ -189,7 +189,19 @@ static value pairwise_eval(vm *v, int nargs, value *args, int mode) {
                 if (rc == MCU_OK) rc = mcu_matrix_download(tmp, new->elements);
                 if (tmp) mcu_matrix_destroy(tmp);
             }
-            if (rc == MCU_OK) { mc_stat_evals++; mc_stat_pairwise++; if (s) mc_stat_devops++; return bind_result(v, new); }
+            if (rc == MCU_OK) {
+                mc_stat_evals++; mc_stat_pairwise++;
+                if (s) mc_stat_devops++;
+                value ours = bind_result(v, new);
+                if (!mc_verify) return ours;
+                /* self-check mode (morphocuda.c): the module's own loop on the same inputs, its result returned */
+                int handle = morpho_retainobjects(v, 1, &ours);
+                shadow_flush_args(nargs, args);
+                bool ok = morpho_invoke(v, self, orig, nargs, args + 1, &ret);
+                if (ok) mc_verify_record("PairwisePotential", mode == MCU_GRADIENT ? "gradient" : "integrand", ours, ret);
+                morpho_releaseobjects(v, handle);
+                return ok ? ret : MORPHO_NIL;
+            }
             if (s) shadow_drop(shadow_find(new));
             object_free((object *) new);
             mc_log("pairwise not accelerated:", mcu_last_error());

@@ -241,6 +241,66 @@ static mcu_field *field_get(objectfield *fld, mc_mirror *mr) {
     return fm->f;
 }
 
+/* ------------------------------------------------------------------ self-check mode */
+
+/* MORPHO_CUDA_VERIFY=1: every evaluation the device handled is ALSO run through the saved reference builtin on the same
+ * inputs; the two results are compared (scalars: relative difference; matrices and fields: max |difference| over max
+ * |reference|), the worst difference per Class.method is reported at exit, and the REFERENCE's result is what the script
+ * receives — so a long optimisation follows the stock trajectory exactly while each of its thousands of evaluations
+ * is checked.  (Optimisers amplify last-digit differences of finite-difference gradients: examples/tactoid reaches
+ * different refined meshes even between `-w0` and `-w4` of the stock reference, so end results cannot be compared.) */
+#define MC_MAXVERIFY 64
+static bool mc_verify = false;
+static struct { char name[48]; long n, mismatched; double worst; } mc_verify_tab[MC_MAXVERIFY];
+static int mc_nverify = 0;
+
+static double mc_verify_arrays(const double *a, const double *b, size_t n) {
+    double num = 0.0, den = 0.0;
+    for (size_t i = 0; i < n; i++) { double d = fabs(a[i] - b[i]); if (d > num || d != d) num = d; if (fabs(b[i]) > den) den = fabs(b[i]); }
+    if (num != num) return INFINITY;
+    return den > 0.0 ? num / den : (num == 0.0 ? 0.0 : INFINITY);
+}
+
+static void mc_verify_record(const char *cls, const char *meth, value ours, value ref) {
+    double err = INFINITY;
+    double x, y;
+    if (MORPHO_ISMATRIX(ours) && MORPHO_ISMATRIX(ref)) {
+        shadow_flush_value(ours); shadow_flush_value(ref);
+        objectmatrix *a = MORPHO_GETMATRIX(ours), *b = MORPHO_GETMATRIX(ref);
+        if (a->nrows == b->nrows && a->ncols == b->ncols) err = mc_verify_arrays(a->elements, b->elements, (size_t) a->nrows * a->ncols);
+    } else if (MORPHO_ISFIELD(ours) && MORPHO_ISFIELD(ref)) {
+        objectfield *a = MORPHO_GETFIELD(ours), *b = MORPHO_GETFIELD(ref);
+        if (a->data.nrows == b->data.nrows) err = mc_verify_arrays(a->data.elements, b->data.elements, (size_t) a->data.nrows);
+    } else if (morpho_valuetofloat(ours, &x) && morpho_valuetofloat(ref, &y)) {
+        err = fabs(x - y) / (fabs(y) > 1e-300 ? fabs(y) : 1e-300);
+        if (x == y) err = 0.0;
+    } else if (MORPHO_ISNIL(ours) && MORPHO_ISNIL(ref)) err = 0.0;
+    char name[48];
+    snprintf(name, sizeof(name), "%s.%s", cls, meth);
+    int k = 0;
+    while (k < mc_nverify && strcmp(mc_verify_tab[k].name, name)) k++;
+    if (k == mc_nverify && mc_nverify < MC_MAXVERIFY) { memset(&mc_verify_tab[k], 0, sizeof(mc_verify_tab[k])); strcpy(mc_verify_tab[k].name, name); mc_nverify++; }
+    if (k < mc_nverify) {
+        mc_verify_tab[k].n++;
+        if (!(err <= mc_verify_tab[k].worst)) mc_verify_tab[k].worst = err;
+        if (!(err < INFINITY)) mc_verify_tab[k].mismatched++;
+    }
+}
+
+static value mc_verified(vm *v, const char *cls, const char *meth, value ours, builtinfunction orig, int nargs, value *args) {
+    int handle = MORPHO_ISOBJECT(ours) ? morpho_retainobjects(v, 1, &ours) : -1;
+    value ref = orig(v, nargs, args);
+    mc_verify_record(cls, meth, ours, ref);
+    if (handle >= 0) morpho_releaseobjects(v, handle);
+    return ref;
+}
+
+static void mc_verify_report(void) {
+    for (int k = 0; k < mc_nverify; k++)
+        fprintf(stderr, "[morphocuda verify] %s evaluations %ld worst %.3e shape-or-type mismatches %ld\n", mc_verify_tab[k].name,
+                mc_verify_tab[k].n, mc_verify_tab[k].worst, mc_verify_tab[k].mismatched);
+}
+
 /* ------------------------------------------------------------------ the veneers */
 
 /* ids of a Selection for grade g: the integer keys of sel->selected[g] (functional.c:226-229) */
@@ -464,7 +524,7 @@ static bool mc_eval_props(vm *v, int nargs, value *args, int functional, int mod
     static builtinfunction orig_##cls##_##meth = NULL; \
     static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
         value out; \
-        if (mc_eval_props(v, nargs, args, FID, MODE, &out)) return out; \
+        if (mc_eval_props(v, nargs, args, FID, MODE, &out)) return mc_verify ? mc_verified(v, #cls, #meth, out, orig_##cls##_##meth, nargs, args) : out; \
         mc_stat_fallbacks++; \
         return orig_##cls##_##meth(v, nargs, args); \
     }
@@ -543,7 +603,7 @@ static bool mc_eval_equielement(vm *v, int nargs, value *args, int mode, value *
     static builtinfunction orig_EquiElement_##meth = NULL; \
     static value mc_EquiElement_##meth(vm *v, int nargs, value *args) { \
         value out; \
-        if (mc_eval_equielement(v, nargs, args, MODE, &out)) return out; \
+        if (mc_eval_equielement(v, nargs, args, MODE, &out)) return mc_verify ? mc_verified(v, "EquiElement", #meth, out, orig_EquiElement_##meth, nargs, args) : out; \
         mc_stat_fallbacks++; \
         return orig_EquiElement_##meth(v, nargs, args); \
     }
@@ -706,7 +766,7 @@ static bool mc_eval_scalarpotential(vm *v, int nargs, value *args, int mode, val
     static builtinfunction orig_ScalarPotential_##meth = NULL; \
     static value mc_ScalarPotential_##meth(vm *v, int nargs, value *args) { \
         value out; \
-        if (mc_eval_scalarpotential(v, nargs, args, MODE, &out)) return out; \
+        if (mc_eval_scalarpotential(v, nargs, args, MODE, &out)) return mc_verify ? mc_verified(v, "ScalarPotential", #meth, out, orig_ScalarPotential_##meth, nargs, args) : out; \
         mc_stat_fallbacks++; \
         return orig_ScalarPotential_##meth(v, nargs, args); \
     }
@@ -718,7 +778,7 @@ MC_SVENEER(gradient, MCU_GRADIENT)
     static builtinfunction orig_##cls##_##meth = NULL; \
     static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
         value out; \
-        if (mc_eval_integral(v, nargs, args, GRADE, MODE, &out)) return out; \
+        if (mc_eval_integral(v, nargs, args, GRADE, MODE, &out)) return mc_verify ? mc_verified(v, #cls, #meth, out, orig_##cls##_##meth, nargs, args) : out; \
         mc_stat_fallbacks++; \
         return orig_##cls##_##meth(v, nargs, args); \
     }
@@ -735,7 +795,7 @@ MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, fieldgradient, MCU_FIELDGRADIENT)
     static builtinfunction orig_##cls##_##meth = NULL; \
     static value mc_##cls##_##meth(vm *v, int nargs, value *args) { \
         value out; \
-        if (mc_eval(v, nargs, args, FID, GRADE, MODE, &out)) return out; \
+        if (mc_eval(v, nargs, args, FID, GRADE, MODE, &out)) return mc_verify ? mc_verified(v, #cls, #meth, out, orig_##cls##_##meth, nargs, args) : out; \
         mc_stat_fallbacks++; \
         return orig_##cls##_##meth(v, nargs, args); \
     }
@@ -1003,6 +1063,7 @@ static void mc_core_initialize(void) {
     const char *dev = getenv("MORPHO_CUDA_DEVICE");
     mc_paranoid = getenv("MORPHO_CUDA_PARANOID") && atoi(getenv("MORPHO_CUDA_PARANOID")) != 0;
     mc_verbose = getenv("MORPHO_CUDA_VERBOSE") && atoi(getenv("MORPHO_CUDA_VERBOSE")) != 0;
+    mc_verify = getenv("MORPHO_CUDA_VERIFY") && atoi(getenv("MORPHO_CUDA_VERIFY")) != 0;
     if (mcu_init(dev ? atoi(dev) : 0) != MCU_OK) {
         /* no CPU path of ours exists: without a usable GPU nothing is patched and the reference runs as shipped */
         fprintf(stderr, "[morphocuda] CUDA unavailable (%s): functionals stay on the reference builtins\n", mcu_last_error());
@@ -1102,6 +1163,7 @@ void morphocuda_finalize(void) {
     if (!mc_core_done) return;
     mc_core_done = false;
     mc_ready = false;
+    if (mc_verify) mc_verify_report();
     while (nshadows > 0) shadow_drop(&shadows[nshadows - 1]);
     while (nmirrors > 0) mirror_drop(nmirrors - 1);
     fields_drop_for(NULL);

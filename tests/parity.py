@@ -35,6 +35,7 @@ EPS_FLOOR = 1e-2       # per-vertex measure: floor as a fraction of the vertex's
 # golden cases; observed values: profiles/r2_parity_errors.json).  Keys: (functional, method).
 FD_TOL = {
     ("AreaEnclosed", "gradient"): 2.6e-11,            # observed 2.6e-12
+    ("EquiElement", "gradient"): 1.0e-11,             # observed 6.1e-15 over the 60 evaluations of the tactoid example
     ("GradSq", "fieldgradient"): 5.0e-10,             # observed 5.0e-11
     ("GradSq", "gradient"): 1.9e-10,                  # observed 1.9e-11
     ("LineCurvatureSq", "gradient"): 8.8e-11,         # observed 8.7e-12

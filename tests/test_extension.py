@@ -289,14 +289,24 @@ def test_thomson_example_as_shipped(tmp_path):
     assert len(hr) == len(hn), (len(hr), len(hn))
 
 
+VERIFY_LINE = re.compile(r"\[morphocuda verify\] (\S+) evaluations (\d+) worst (\S+) shape-or-type mismatches (\d+)")
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="oracle/_ref/examples not built")
 def test_tactoid_example_as_shipped(tmp_path):
     """BASELINE.json config 4's script: examples/tactoid/tactoid.morpho as shipped up to its visualisation block (only
     `import plot` / `import povray` and everything from "// Function to visualize" on are dropped; disk.mesh beside it):
     Nematic + anchoring LineIntegral (closure with tangent()) + Length on the boundary selection, Area constraint, NormSq
-    local constraint, EquiElement regulariser with weights, 3 adaptive refinements, equiangulation.  Every functional call of
-    the run is evaluated on the GPU (cudastats()[3] == 0); the report lines agree with the stock run."""
+    local constraint, EquiElement regulariser with weights, 3 adaptive refinements, equiangulation.
+
+    The example is chaotic: the stock reference itself ends on different refined meshes with -w0 and -w4 (99 / 91
+    vertices), because the optimisers amplify last-digit differences of the finite-difference gradients.  So (1) a plain
+    run through the extension must evaluate EVERY functional call on the GPU (cudastats()[3] == 0) and agree with the
+    stock run over the first field + shape stage (6 printed digits); (2) a run in self-check mode
+    (MORPHO_CUDA_VERIFY=1: every device evaluation is compared with the saved reference builtin on the same inputs and the
+    reference's result is returned) must reproduce the stock output character for character, with the worst
+    difference of each of its ~42 000 evaluations inside the tolerances of tests/parity.py."""
     import shutil
     text = open(os.path.join(EXAMPLES, "tactoid", "tactoid.morpho")).read()
     text = text[:text.index("// Function to visualize a director field")].replace("import plot\n", "").replace("import povray\n", "")
@@ -308,16 +318,26 @@ def test_tactoid_example_as_shipped(tmp_path):
     stats = [float(x) for x in NUM.findall(new[-1])]
     print("tactoid as shipped: cudastats", stats)
     assert stats[0] > 1000 and stats[3] == 0, (stats, err[-2000:])       # evaluations on the GPU, none left to the reference
-    i = ref.index([l for l in ref if l.startswith("final")][0])
-    assert ref[i] == new[i], (ref[i], new[i])                             # same refined mesh
-    er, en = [float(x) for x in ref[i + 1:]], [float(x) for x in new[i + 1:-1]]
-    worst = max(abs(a - b) / abs(a) for a, b in zip(er, en))
-    from tests.parity import record
-    record("extension", "tactoid_as_shipped.final_energies", worst)
-    print(f"tactoid as shipped: final energy contributions {en}, worst relative difference {worst:.2e}")
-    assert worst <= 1e-6, worst
-    assert len(ref) == len(new) - 1
-    compare(ref[:i], new[:i], 2e-5)                                       # 6 significant digits printed
+    assert stats[4] < stats[0] / 2, stats                                 # fields are uploaded when written, not per evaluation
+    compare(ref[:30], new[:30], 2e-5)                                     # regularise + field stage + 14 shape iterations
+    chk, err = run("import morphocuda\n" + text + tail, tmp_path, "verify.morpho", {"MORPHO_CUDA_VERIFY": "1"})
+    assert chk == ref                                                     # the reference's results were returned: same trajectory
+    from tests.parity import FD_TOL, TOL_EXACT, TOL_FD, record
+    seen = {}
+    for name, n, worst, bad in VERIFY_LINE.findall(err):
+        seen[name] = (int(n), float(worst), int(bad))
+        record("extension", "tactoid_verify." + name, float(worst))
+    print("tactoid as shipped, self-check:", seen)
+    assert sum(n for n, _, _ in seen.values()) > 30000, seen
+    for name, (n, worst, bad) in seen.items():
+        cls, meth = name.split(".")
+        analytic = cls in ("Length", "Area") or meth in ("total", "integrand")
+        tol = TOL_EXACT if analytic else min(TOL_FD, FD_TOL.get((cls, meth), TOL_FD))
+        assert bad == 0 and worst <= tol, (name, n, worst, tol)
+    for needed in ("Nematic.total", "Nematic.gradient", "Nematic.fieldgradient", "Nematic.integrand", "LineIntegral.total",
+                   "LineIntegral.gradient", "LineIntegral.fieldgradient", "Length.gradient", "Area.gradient", "NormSq.fieldgradient",
+                   "EquiElement.total", "EquiElement.gradient"):
+        assert needed in seen, (needed, sorted(seen))
 
 
 @pytest.mark.gpu
