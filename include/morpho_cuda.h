@@ -73,7 +73,8 @@ enum {
 enum {
     MCU_PATH_AUTO = 0,
     MCU_PATH_GATHER = 1,   /* CSR-transpose vertex gather, reference summation order */
-    MCU_PATH_PATCH = 2     /* shared-memory patch kernel (triangles; analytic gradients) */
+    MCU_PATH_PATCH = 2,    /* shared-memory patch kernel (triangles; analytic gradients) */
+    MCU_PATH_BLOCK = 3     /* shared-memory block kernel (any grade, selections; analytic gradients) */
 };
 
 typedef struct mcu_mesh mcu_mesh;           /* device mirror of objectmesh      (mesh.h:25-31)      */
@@ -305,6 +306,12 @@ int mcu_debug_dfma_peak(double *tflops);
  *      Output arrays may be NULL. ---- */
 int mcu_debug_patch_plan(int nv, int nel, const int *rix, const double *vert, int max_owned, long counts[10],
                          int *hdr_out, int *runs_out, unsigned *tab_out);
+
+/* the block decomposition of the generic owner-computes gradient kernel (mcu_block.cu), pure host code: counts = {blocks,
+ * local vertices, entries, vertices with elements, 1 if every vertex has one}; hdr_out receives 14 ints per block
+ * {loc_off, n_local, n_owned, 0, ent_off[8], deg[8] packed in 2 ints}.  eids: selected element ids or NULL. */
+int mcu_debug_block_plan(int nv, int dim, int n, int nvper, const int *rix, const int *eids, const double *vert, long counts[5],
+                         int *hdr_out, int *loc_out, unsigned *ent_out);
 
 /* timeline diagnostics of the patch kernel (measurement aid): dev_buf receives, per consumer warp of every CTA,
  * {cycles waiting for data, cycles alive}; NULL disarms. */

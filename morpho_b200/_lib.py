@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MORPHO_CUDA_LIB", os.path.join(HERE, "lib", "libmorph
 MCU_OK, MCU_ERR_ARGS, MCU_ERR_ELNOTFOUND, MCU_ERR_DEGENERATE, MCU_ERR_VOLENCLZERO, \
     MCU_ERR_UNSUPPORTED, MCU_ERR_CUDA, MCU_ERR_ALLOC = range(8)
 MCU_TOTAL, MCU_INTEGRAND, MCU_GRADIENT, MCU_FIELDGRADIENT = range(4)
-MCU_PATH_AUTO, MCU_PATH_GATHER, MCU_PATH_PATCH = range(3)
+MCU_PATH_AUTO, MCU_PATH_GATHER, MCU_PATH_PATCH, MCU_PATH_BLOCK = range(4)
 MCU_PW_COULOMB, MCU_PW_LAURENT, MCU_PW_YUKAWA, MCU_PW_PROGRAM = range(4)
 
 FUNCTIONAL_IDS = {
@@ -134,6 +134,7 @@ def lib():
         "mcu_halo_destroy": (C.c_int, [vp]),
         "mcu_debug_patch_profile": (C.c_int, [vp]),
         "mcu_debug_patch_plan": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_long), vp, vp, vp]),
+        "mcu_debug_block_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_long), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

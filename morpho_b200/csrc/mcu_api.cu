@@ -14,6 +14,7 @@
 
 #include "mcu_host.h"
 #include "mcu_patch.h"
+#include "mcu_block.h"
 
 long g_mcu_launches = 0;
 
@@ -121,9 +122,11 @@ int mcu_init(int device) {
     return MCU_OK;
 }
 
+static void graveyard_purge(const struct mcu_mesh *m);
 int mcu_finalize(void) {
     if (!g_inited) return MCU_OK;
     cudaStreamSynchronize(g_stream);
+    graveyard_purge(nullptr);
     if (g_scratch) cudaFree(g_scratch);
     g_scratch = nullptr; g_scratch_bytes = 0;
     if (g_flush_buf) cudaFree(g_flush_buf);
@@ -180,12 +183,14 @@ static void conn_free(mcu_mesh *m, McuConn &c) {
     if (c.d_tptr) cudaFree(c.d_tptr);
     if (c.d_tidx) cudaFree(c.d_tidx);
     if (c.patches) { mcu_patchset_free(c.patches); c.patches = nullptr; }
+    if (c.blocks) { mcu_blockset_free(c.blocks); c.blocks = nullptr; }
     c = McuConn();
 }
 
 int mcu_mesh_destroy(mcu_mesh *m) {
     if (!m) return MCU_OK;
     cudaStreamSynchronize(g_stream);
+    graveyard_purge(m);
     for (int g = 0; g < 4; g++) conn_free(m, m->conn[g]);
     cudaFree(m->d_vert_own); cudaFree(m->d_partials); cudaFree(m->d_scalar); cudaFree(m->d_flags);
     if (m->d_result) cudaFree(m->d_result);
@@ -343,6 +348,25 @@ double *mcu_field_device(mcu_field *f) { return f ? f->d_data : nullptr; }
 
 /* ------------------------------------------------------------------ Selection */
 
+/* Callers that follow the reference's calling convention (the extension: a Selection object arrives with every call,
+ * functional.c:82-102) create and destroy a selection mirror per evaluation.  Destroyed mirrors rest in a small
+ * graveyard; a new selection with the same mesh, grade, connectivity version and ids takes its predecessor's device
+ * arrays and block decomposition over instead of building them again. */
+#define MCU_SEL_GRAVEYARD 8
+static mcu_selection *g_sel_graveyard[MCU_SEL_GRAVEYARD];
+static int g_sel_buried = 0;
+static void selection_release(mcu_selection *s);
+
+static void graveyard_purge(const mcu_mesh *m) {       // m == nullptr: everything
+    int k = 0;
+    for (int i = 0; i < g_sel_buried; i++) {
+        mcu_selection *s = g_sel_graveyard[i];
+        if (!m || s->m == m) { selection_release(s); delete s; }
+        else g_sel_graveyard[k++] = s;
+    }
+    g_sel_buried = k;
+}
+
 mcu_selection *mcu_selection_create(mcu_mesh *m, int g, int n, const int *ids) {
     if (!m || g < 0 || g > 3 || n < 0 || (n > 0 && !ids)) { mcu_set_error("bad selection arguments"); return nullptr; }
     int limit = (g == 0 ? m->nv : (m->conn[g].present ? m->conn[g].nel : 0));
@@ -351,6 +375,14 @@ mcu_selection *mcu_selection_create(mcu_mesh *m, int g, int n, const int *ids) {
     s->ids.assign(ids, ids + n);
     std::sort(s->ids.begin(), s->ids.end());
     s->ids.erase(std::unique(s->ids.begin(), s->ids.end()), s->ids.end());
+    for (int i = 0; i < g_sel_buried; i++) {
+        mcu_selection *old = g_sel_graveyard[i];
+        if (old->m == m && old->g == g && old->conn_version == m->conn_version && old->ids == s->ids) {
+            g_sel_graveyard[i] = g_sel_graveyard[--g_sel_buried];
+            delete s;
+            return old;
+        }
+    }
     for (int id : s->ids)
         if (id < 0 || id >= limit) { mcu_set_error("selected id %d out of range for grade %d", id, g); delete s; return nullptr; }
     s->conn_version = m->conn_version;
@@ -363,13 +395,20 @@ static void selection_release(mcu_selection *s) {
     if (s->d_tidx) cudaFree(s->d_tidx);
     if (s->d_mask) cudaFree(s->d_mask);
     s->d_eids = s->d_tptr = s->d_tidx = nullptr; s->d_mask = nullptr;
+    if (s->blocks) { mcu_blockset_free(s->blocks); s->blocks = nullptr; }
+    s->block_failed = false;
 }
 
 int mcu_selection_destroy(mcu_selection *s) {
     if (!s) return MCU_OK;
     cudaStreamSynchronize(g_stream);
-    selection_release(s);
-    delete s;
+    if (g_sel_buried == MCU_SEL_GRAVEYARD) {                 // the oldest goes for good
+        selection_release(g_sel_graveyard[0]);
+        delete g_sel_graveyard[0];
+        for (int i = 1; i < g_sel_buried; i++) g_sel_graveyard[i - 1] = g_sel_graveyard[i];
+        g_sel_buried--;
+    }
+    g_sel_graveyard[g_sel_buried++] = s;
     return MCU_OK;
 }
 
@@ -464,6 +503,25 @@ int mcu_ensure_patches(mcu_mesh *m, int g) {
     if (!c.patches) c.patch_failed = true;
     return c.patches ? MCU_OK : MCU_ERR_UNSUPPORTED;
 }
+// Block decomposition of grade g (of the selected elements if sel): built on first use from the current positions,
+// kept until the connectivity (or the selection) changes.  nullptr: the planner refused (remembered).
+static McuBlockSet *mcu_ensure_blocks(mcu_mesh *m, int g, mcu_selection *sel) {
+    McuConn &c = m->conn[g];
+    if (!c.present || m->vert_version == 0) return nullptr;
+    McuBlockSet **slot = sel ? &sel->blocks : &c.blocks;
+    bool *failed = sel ? &sel->block_failed : &c.block_failed;
+    if (sel && sel->blocks && sel->blocks_version != m->conn_version) { mcu_blockset_free(sel->blocks); sel->blocks = nullptr; sel->block_failed = false; }
+    if (*slot) return *slot;
+    if (*failed) return nullptr;
+    if (cudaStreamSynchronize(g_stream) != cudaSuccess) return nullptr;
+    std::vector<double> hv((size_t) m->nv * m->dim);
+    if (cudaMemcpy(hv.data(), m->d_vert, sizeof(double) * hv.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+    *slot = mcu_blockset_build(m->nv, m->dim, sel ? (int) sel->ids.size() : c.nel, c.nvper, c.h_rix.data(), sel ? sel->ids.data() : nullptr, hv.data(), g_stream);
+    if (!*slot) *failed = true;
+    if (sel) sel->blocks_version = m->conn_version;
+    return *slot;
+}
+
 extern "C" {
 
 static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, double *d_out) {
@@ -591,6 +649,14 @@ static int eval_impl(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, i
                     e = mcu_patch_gradient(F, *c.patches, m->d_vert, d_out, m->d_flags, st, pushing ? &push : nullptr);
                     break;
                 }
+            }
+            // any grade / selections: the shared-memory block kernel (mcu_block.cu); small meshes stay on the gather kernel
+            const bool blockable = fast && g >= 1 && (F == MCU_F_LENGTH || F == MCU_F_AREA || F == MCU_F_VOLUMEENCLOSED || F == MCU_F_VOLUME);
+            if (path == MCU_PATH_BLOCK && !blockable) { mcu_set_error("block path not applicable"); return MCU_ERR_UNSUPPORTED; }
+            if (blockable && (path == MCU_PATH_BLOCK || (path == MCU_PATH_AUTO && v.n >= mcu_opt("block_min_elements", 32768)))) {
+                McuBlockSet *bs = mcu_ensure_blocks(m, g, sel);
+                if (bs) { e = mcu_block_gradient(F, *bs, m->d_vert, m->nv, m->dim, d_out, m->d_flags, st); break; }
+                if (path == MCU_PATH_BLOCK) return MCU_ERR_UNSUPPORTED;
             }
             e = fast ? mcu_fast_gradient(p, v, d_out, m->d_flags, st) : mcu_strict_gradient(p, v, d_out, m->d_flags, st);
             break;

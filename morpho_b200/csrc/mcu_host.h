@@ -6,6 +6,7 @@
 #include "mcu_kernels.h"
 
 struct McuPatchSet;
+struct McuBlockSet;
 
 // element → vertex incidence of one grade: the CCS arrays of mesh_getconnectivityelement(m,0,g)
 // (mesh.c:296-307; cptr is implicit, e*(g+1)) plus derived device structures.
@@ -17,6 +18,8 @@ struct McuConn {
     int *d_tptr = nullptr, *d_tidx = nullptr;   // vertex → element transpose (lazily built)
     McuPatchSet *patches = nullptr;  // shared-memory patch decomposition (lazily built, triangles)
     bool patch_failed = false;       // the planner refused this connectivity: do not plan again until it changes
+    McuBlockSet *blocks = nullptr;   // block decomposition of the generic owner-computes gradient kernel (mcu_block.cu), lazily built
+    bool block_failed = false;
 };
 
 struct mcu_mesh {
@@ -49,6 +52,9 @@ struct mcu_selection {
     int *d_tptr = nullptr, *d_tidx = nullptr;   // transpose restricted to the selected elements
     unsigned char *d_mask = nullptr; // grade 0 only
     long conn_version = -1;
+    McuBlockSet *blocks = nullptr;   // block decomposition restricted to the selected elements (lazily built)
+    bool block_failed = false;
+    long blocks_version = -1;
 };
 
 void mcu_set_error(const char *fmt, ...);

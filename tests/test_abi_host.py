@@ -192,3 +192,126 @@ def test_patch_triangle_lists_cover_every_triangle_once(L, f, max_owned):
             assert t in key and key[t] not in seen
             seen[key[t]] = pi
     assert len(seen) == c.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Block decomposition of the generic owner-computes gradient kernel (morpho_b200/csrc/mcu_block.cu): host logic.
+# ---------------------------------------------------------------------------------------------------------------
+
+def _block_plan(L, v, conn, eids=None):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    e = None if eids is None else np.ascontiguousarray(eids, dtype=np.int32)
+    n = conn.shape[0] if e is None else len(e)
+    counts = (C.c_long * 5)()
+    args = (v.shape[0], v.shape[1], n, conn.shape[1], conn.ctypes.data, None if e is None else e.ctypes.data, v.ctypes.data, counts)
+    assert L.mcu_debug_block_plan(*args, None, None, None) == 0
+    nb, nloc, nent, nact, allact = (int(x) for x in counts)
+    hdr = np.zeros((nb, 14), dtype=np.int32)
+    loc = np.zeros(max(nloc, 1), dtype=np.int32)
+    ent = np.zeros(max(nent, 1), dtype=np.uint32)
+    assert L.mcu_debug_block_plan(*args, hdr.ctypes.data, loc.ctypes.data, ent.ctypes.data) == 0
+    return hdr, loc[:nloc], ent[:nent], nact, bool(allact)
+
+
+def _emulate_block_gradient(name, v, hdr, loc, ent):
+    """What k_block_grad computes, in numpy, straight from the plan: every owned vertex walks its entries."""
+    nv, dim = v.shape
+    x3 = np.concatenate([v, np.zeros((nv, 3 - dim))], axis=1)
+    out = np.zeros((nv, 3))
+    written = np.zeros(nv, dtype=int)
+    ntets = np.zeros(nv, dtype=int)
+    for h in hdr:
+        loc_off, n_local, n_owned = int(h[0]), int(h[1]), int(h[2])
+        ent_off = h[4:12].view(np.uint32)
+        deg = h[12:14].view(np.uint8)
+        assert n_owned <= 256 and n_local <= 1023 and n_owned <= n_local
+        ids = loc[loc_off: loc_off + n_local]
+        assert len(set(ids.tolist())) == n_local                        # every local vertex has one slot
+        assert np.all(np.diff(ids[:n_owned]) > 0) and np.all(np.diff(ids[n_owned:]) > 0)
+        X = x3[ids]
+        for t in range(n_owned):
+            w, lane = divmod(t, 32)
+            p = X[t]
+            acc = np.zeros(3)
+            if name == "Volume":
+                # tetrahedra: 16-bit entries walk the link of the vertex as triangle strips (mcu_block.cu link_strips)
+                e16 = ent.view(np.uint16)
+                a = b = c = np.zeros(3)
+                ntri = 0
+                assert int(ent_off[w]) % 128 == 0                            # 8-byte loads of four entries per lane
+                for j in range(4 * int(deg[w])):                               # deg counts groups of four entries
+                    e = int(e16[int(ent_off[w]) + ((j // 4) * 32 + lane) * 4 + (j & 3)])
+                    op, s = e >> 10, e & 1023
+                    a, b, c = (a if op == 1 else b), c, X[s]
+                    if op < 2:
+                        N = np.cross(b - a, c - a)
+                        acc += np.sign((p - a) @ N) * N / 6
+                        ntri += 1
+                out[ids[t]] = acc
+                written[ids[t]] += 1
+                ntets[ids[t]] = ntri
+                continue
+            for j in range(int(deg[w])):
+                e = int(ent[int(ent_off[w]) + 32 * j + lane])
+                if e == 0xffffffff:
+                    continue
+                a, b, c = X[e & 1023], X[(e >> 10) & 1023], X[(e >> 20) & 1023]
+                if name == "Length":
+                    acc += (p - a) / np.linalg.norm(p - a)
+                elif name == "Area":
+                    N = np.cross(a - p, b - p)
+                    acc += np.cross(N, (b - p) - (a - p)) / (2 * np.linalg.norm(N))
+                elif name == "VolumeEnclosed":
+                    cx = np.cross(a, b)
+                    acc += np.sign(p @ cx) * cx / 6
+                else:
+                    N = np.cross(b - a, c - a)
+                    acc += np.sign((p - a) @ N) * N / 6
+            out[ids[t]] = acc
+            written[ids[t]] += 1
+    if name == "Volume":
+        return out[:, :dim], written, ntets
+    return out[:, :dim], written
+
+
+@pytest.mark.parametrize("case", ["tets", "tets_selected", "triangles_selected", "lines_2d", "sphere_volencl"])
+def test_block_plan_reproduces_the_oracle_gradient(L, case):
+    """The plan alone determines the result: emulating the kernel from (headers, local lists, entries) gives the
+    oracle's gradient (1e-12), every vertex with elements is owned exactly once, and vertices without (selected)
+    elements are owned by nobody."""
+    from oracle.oracle import FunctionalSpec, Oracle
+    from morpho_b200 import meshgen as mg
+    O = Oracle()
+    rng = np.random.Generator(np.random.PCG64(7))
+    sel = None
+    if case in ("tets", "tets_selected"):
+        v, c = mg.tet_cube(7)
+        v = v + 0.02 * rng.uniform(-1, 1, size=v.shape)
+        name, g = "Volume", 3
+        if case == "tets_selected":
+            sel = np.sort(rng.choice(c.shape[0], size=c.shape[0] // 2, replace=False)).astype(np.int32)
+    elif case == "triangles_selected":
+        v, c = mg.icosphere(9)
+        v = mg.perturb_radially(v, 0.05, 3)
+        sel = np.sort(rng.choice(c.shape[0], size=c.shape[0] // 3, replace=False)).astype(np.int32)
+        name, g = "Area", 2
+    elif case == "lines_2d":
+        v, c = mg.polyline_loop(300, 2, 5)
+        name, g = "Length", 1
+    else:
+        v, c = mg.icosphere(12)
+        v = mg.perturb_radially(v, 0.05, 4)
+        name, g = "VolumeEnclosed", 2
+    hdr, loc, ent, nact, allact = _block_plan(L, v, c, sel)
+    res = _emulate_block_gradient(name, v, hdr, loc, ent)
+    got, written = res[0], res[1]
+    if name == "Volume":                                   # every incident tetrahedron is visited exactly once by the strips
+        cnt = np.bincount((c if sel is None else c[sel]).ravel(), minlength=v.shape[0])
+        assert np.array_equal(res[2], cnt)
+    used = np.zeros(v.shape[0], dtype=bool)
+    used[np.unique(c if sel is None else c[sel])] = True
+    assert np.array_equal(written == 1, used) and written.max() <= 1 and nact == used.sum() and allact == bool(used.all())
+    want = O.gradient(v, {g: c}, FunctionalSpec(name), sel)
+    err = np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max()
+    assert err <= 1e-12, err

@@ -153,6 +153,16 @@ def test_config5_tet_cube_50m(mb, oracle):
     assert np.abs(g[inner]).max() <= 1e-12 * np.abs(g).max() * 10
     assert np.abs(g.sum(axis=0)).max() <= 1e-9 * np.abs(g).max()
     assert abs((g * v).sum() - 3.0 * V) <= 1e-11
+    # the gradient above came from the block kernel (mcu_block.cu: AUTO takes it for large meshes); the CSR-transpose gather
+    # visits the same elements in the same order with the reference's own formulas
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_GATHER)
+    g_gather = vol.gradient(m)
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+    assert rel_array(g, g_gather, rows=3) <= TOL_EXACT
+    # rows of boundary vertices are O(1/n^2): compare them vertex by vertex
+    bnd = ~inner
+    assert (np.linalg.norm(g[bnd] - g_gather[bnd], axis=1) / np.linalg.norm(g_gather[bnd], axis=1)).max() <= 1e-11
+    del g_gather
     vi = vol.integrand(m)
     assert abs(vi.sum() - V) <= 1e-12
     # a 5-component field: GradSq is quadratic in q, zero for constants, exact for linear fields

@@ -75,6 +75,39 @@ def test_cuda_matches_reference_golden(mb, case):
     print({k: f"{v:.1e}" for k, v in worst.items()})
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if any(ev["f"]["name"] in ANALYTIC for ev in c["evals"])],
+                         ids=[c["name"] for c in CASES if any(ev["f"]["name"] in ANALYTIC for ev in c["evals"])])
+def test_block_kernel_matches_reference_golden(mb, case):
+    """The shared-memory block kernel (mcu_block.cu; gradient_path = MCU_PATH_BLOCK) on every analytic gradient of the
+    golden cases — lines, triangles, tetrahedra, 2-D and 3-D, with and without Selections — at 1e-12, norm-wise and per
+    vertex, and bit-identical rows where no (selected) element touches a vertex."""
+    gold = np.load(os.path.join(GOLD, case["name"] + ".npz"))
+    mesh, fields = _build(mb, case)
+    mb.set_option("gradient_path", mb._lib.MCU_PATH_BLOCK)
+    try:
+        n = 0
+        for i, ev in enumerate(case["evals"]):
+            name = ev["f"]["name"]
+            if name not in ANALYTIC or ev["method"] != "gradient":
+                continue
+            key = eval_key(i, ev)
+            got = _cuda_eval(mb, mesh, fields, ev)
+            assert got is not None, key
+            err = measure(ev, got, gold[key], case)
+            record("golden_block", f"{name}.gradient", err)
+            assert err <= TOL_EXACT, f"{case['name']}:{key} err {err:.3e}"
+            g = {"Length": 1, "Area": 2, "VolumeEnclosed": 2, "Volume": 3}[name]
+            conn = case["grades"][g] if "sel" not in ev else case["grades"][g][ev["sel"][1]]
+            S = contribution_norm_sum(name, case["vert"], conn)
+            pv = rel_pervertex(got, gold[key], S)
+            record("golden_block_pervertex", f"{name}.gradient", pv)
+            assert pv <= TOL_EXACT, f"{case['name']}:{key} per-vertex err {pv:.3e}"
+            n += 1
+        assert n > 0
+    finally:
+        mb.set_option("gradient_path", mb._lib.MCU_PATH_AUTO)
+
+
 @pytest.mark.parametrize("f", [1, 7, 40])
 def test_transpose_bit_exact(mb, oracle, f):
     from morpho_b200 import meshgen as mg
