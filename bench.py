@@ -141,7 +141,7 @@ def run_reference(args):
         return 0
     from morpho_b200.partition import build_rank_mesh
     world = max(int(args.gpus), 1)
-    f = frequency_for(world, args.freq)
+    f = frequency_for(world, args.freq) if args.scaling != "strong" else args.freq
     t0 = time.time()
     part = build_rank_mesh(f, 0, 1) if world == 1 else _rank0_range(f, world)
     vert, conn = part.vert, part.conn
@@ -314,72 +314,83 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     _lib.check(L.mcu_set_stream(stream.cuda_stream))
 
-    f = frequency_for(world, args.freq)
-    t0 = time.time()
-    part = build_rank_mesh(f, rank, world)       # this rank's element range of the global sphere (+ shared-vertex maps)
-    vert, conn = part.vert, part.conn
-    nel_local, nel_global = conn.shape[0], part.nel_global
-    log(f"[rank {rank}] f={f}: {nel_local} of {nel_global} triangles, {vert.shape[0]} vertices, "
-        f"{part.n_shared} shared ({time.time() - t0:.1f}s)")
-
-    if args.patch_owned:
-        mb.set_option("patch_max_owned", args.patch_owned)
-    for kv in args.opt:
-        k_, v_ = kv.split("=")
-        mb.set_option(k_, int(v_))
-    mesh = mb.Mesh(vert, faces=conn)
-    area, vol = mb.Area()._desc(), mb.VolumeEnclosed()._desc()
     import ctypes as C
-    nout = vert.size
-    g_area = torch.empty(nout, dtype=torch.float64, device="cuda")
-    g_vol = torch.empty(nout, dtype=torch.float64, device="cuda")
-    exch = None
-    if world > 1:
-        from morpho_b200.partition import PeerExchange
-        exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
-        if not args.no_fused_push and args.exchange != "nccl":
-            exch.attach(mesh)                             # the gradient kernels store the shared rows into the peers' buffers themselves
+    from types import SimpleNamespace
 
-    fused = exch is not None and not args.no_fused_push and args.exchange != "nccl"
+    def build_workload(f):
+        """This rank's element range of the icosphere of frequency f with its mesh mirror, the output rows, the
+        shared-row exchange (N > 1) and the step itself."""
+        t0 = time.time()
+        part = build_rank_mesh(f, rank, world)       # this rank's element range of the global sphere (+ shared-vertex maps)
+        vert, conn = part.vert, part.conn
+        nel_local, nel_global = conn.shape[0], part.nel_global
+        log(f"[rank {rank}] f={f}: {nel_local} of {nel_global} triangles, {vert.shape[0]} vertices, "
+            f"{part.n_shared} shared ({time.time() - t0:.1f}s)")
 
-    nccl_state = {}
+        if args.patch_owned:
+            mb.set_option("patch_max_owned", args.patch_owned)
+        for kv in args.opt:
+            k_, v_ = kv.split("=")
+            mb.set_option(k_, int(v_))
+        mesh = mb.Mesh(vert, faces=conn)
+        area, vol = mb.Area()._desc(), mb.VolumeEnclosed()._desc()
+        nout = vert.size
+        g_area = torch.empty(nout, dtype=torch.float64, device="cuda")
+        g_vol = torch.empty(nout, dtype=torch.float64, device="cuda")
+        exch = None
+        if world > 1:
+            from morpho_b200.partition import PeerExchange
+            exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
+            if not args.no_fused_push and args.exchange != "nccl":
+                exch.attach(mesh)                             # the gradient kernels store the shared rows into the peers' buffers themselves
 
-    def nccl_exchange():
-        """Comparison arm (--exchange nccl): ONE ncclAllReduce of the packed rows of all shared vertices (zero where this
-        rank does not hold the vertex), then unpack — the collective-library way to do what mcu_halo.cu does."""
-        if not nccl_state:
-            nccl_state["idx"] = torch.as_tensor(part.shared_local, dtype=torch.int64, device="cuda")
-            nccl_state["slot"] = torch.as_tensor(part.shared_slot, dtype=torch.int64, device="cuda")
-            nccl_state["buf"] = torch.zeros((part.n_slots, 6), dtype=torch.float64, device="cuda")
-        idx, slot, buf = nccl_state["idx"], nccl_state["slot"], nccl_state["buf"]
-        buf.zero_()
-        buf.index_copy_(0, slot, torch.cat([g_area.view(-1, 3).index_select(0, idx), g_vol.view(-1, 3).index_select(0, idx)], dim=1))
-        dist.all_reduce(buf)
-        rows = buf.index_select(0, slot)
-        g_area.view(-1, 3).index_copy_(0, idx, rows[:, :3].contiguous())
-        g_vol.view(-1, 3).index_copy_(0, idx, rows[:, 3:].contiguous())
+        fused = exch is not None and not args.no_fused_push and args.exchange != "nccl"
 
-    def step_device(evs=None):
-        if evs: evs[0].record(stream)
-        if fused:
-            exch.bind(0)
-        _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
-        if exch is not None and args.exchange == "overlap":
-            exch.exchange_async(0, g_area.data_ptr())     # Area's shared rows complete underneath the next kernel
-        if evs: evs[1].record(stream)
-        if fused:
-            exch.bind(1)
-        _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
-        if evs: evs[2].record(stream)
-        if exch is not None:
-            if args.exchange == "overlap":
-                exch.exchange_async(1, g_vol.data_ptr())
-                exch.join()
-            elif args.exchange == "nccl":
-                nccl_exchange()
-            else:
-                exch(g_area, g_vol)               # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
-        if evs: evs[3].record(stream)
+        nccl_state = {}
+
+        def nccl_exchange():
+            """Comparison arm (--exchange nccl): ONE ncclAllReduce of the packed rows of all shared vertices (zero where this
+            rank does not hold the vertex), then unpack — the collective-library way to do what mcu_halo.cu does."""
+            if not nccl_state:
+                nccl_state["idx"] = torch.as_tensor(part.shared_local, dtype=torch.int64, device="cuda")
+                nccl_state["slot"] = torch.as_tensor(part.shared_slot, dtype=torch.int64, device="cuda")
+                nccl_state["buf"] = torch.zeros((part.n_slots, 6), dtype=torch.float64, device="cuda")
+            idx, slot, buf = nccl_state["idx"], nccl_state["slot"], nccl_state["buf"]
+            buf.zero_()
+            buf.index_copy_(0, slot, torch.cat([g_area.view(-1, 3).index_select(0, idx), g_vol.view(-1, 3).index_select(0, idx)], dim=1))
+            dist.all_reduce(buf)
+            rows = buf.index_select(0, slot)
+            g_area.view(-1, 3).index_copy_(0, idx, rows[:, :3].contiguous())
+            g_vol.view(-1, 3).index_copy_(0, idx, rows[:, 3:].contiguous())
+
+        def step_device(evs=None):
+            if evs: evs[0].record(stream)
+            if fused:
+                exch.bind(0)
+            _lib.check(L.mcu_eval_device(mesh._h, C.byref(area), None, _lib.MCU_GRADIENT, g_area.data_ptr()))
+            if exch is not None and args.exchange == "overlap":
+                exch.exchange_async(0, g_area.data_ptr())     # Area's shared rows complete underneath the next kernel
+            if evs: evs[1].record(stream)
+            if fused:
+                exch.bind(1)
+            _lib.check(L.mcu_eval_device(mesh._h, C.byref(vol), None, _lib.MCU_GRADIENT, g_vol.data_ptr()))
+            if evs: evs[2].record(stream)
+            if exch is not None:
+                if args.exchange == "overlap":
+                    exch.exchange_async(1, g_vol.data_ptr())
+                    exch.join()
+                elif args.exchange == "nccl":
+                    nccl_exchange()
+                else:
+                    exch(g_area, g_vol)               # shared-vertex rows completed over NVLink peer memory (mcu_halo.cu)
+            if evs: evs[3].record(stream)
+        return SimpleNamespace(f=f, part=part, vert=vert, conn=conn, nel_local=nel_local, nel_global=nel_global, mesh=mesh, area=area, vol=vol,
+                               nout=nout, g_area=g_area, g_vol=g_vol, exch=exch, fused=fused, step_device=step_device)
+
+    f = frequency_for(world, args.freq) if args.scaling != "strong" else args.freq
+    W = build_workload(f)
+    part, vert, conn, nel_local, nel_global, mesh, area, vol = W.part, W.vert, W.conn, W.nel_local, W.nel_global, W.mesh, W.area, W.vol
+    nout, g_area, g_vol, exch, fused, step_device = W.nout, W.g_area, W.g_vol, W.exch, W.fused, W.step_device
 
     def barrier():
         if world > 1:
@@ -517,6 +528,40 @@ def run_ours(args):
 
     if exch is not None and exch.status() != 0:
         raise RuntimeError("halo exchange: a peer did not arrive in time")
+
+    # ---- strong scaling (N > 1): the SAME 10M-triangle sphere of BASELINE config 2 cut N ways ----------------
+    strong = None
+    if world > 1 and args.scaling == "both":
+        S = build_workload(args.freq)
+        par_s = None
+        if not args.no_parity:
+            par_s = parity_check(S.part, S.vert, S.conn, S.step_device, S.g_area, S.g_vol, torch, dist, world, rank, barrier)
+            if par_s["max_rel"] > 1e-12 or par_s["max_rel_pervertex"] > 1e-12 or not par_s["shared_rows_bitwise_equal"]:
+                raise SystemExit(f"parity check failed (strong-scaling mesh): {par_s}")
+        for _ in range(max(args.warmup, 3)):
+            S.step_device()
+        barrier()
+        evs_s = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(stream)
+        for k in range(args.steps):
+            S.step_device(evs_s[k])
+        b_.record(stream)
+        barrier()
+        ts = torch.tensor([a_.elapsed_time(b_) / args.steps] +
+                          [float(np.mean([evs_s[k][i].elapsed_time(evs_s[k][i + 1]) for k in range(args.steps)])) for i in range(3)],
+                          dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ts = [float(x) for x in ts.cpu()]
+        if S.exch.status() != 0:
+            raise RuntimeError("halo exchange (strong-scaling mesh): a peer did not arrive in time")
+        strong = {"workload": workload_string(args.freq, world), "value": 2.0 * S.nel_global / (ts[0] * 1e-3) / 1e6, "unit": UNIT,
+                  "ms_per_step": ts[0], "steps": args.steps,
+                  "kernel_ms": {"area_gradient": ts[1], "volumeenclosed_gradient": ts[2], "shared_row_exchange": ts[3]},
+                  "shared_vertices_rank0": int(S.part.n_shared), "parity": par_s,
+                  "note": "total work fixed: compare `value` with the N=1 line's (the driver's SCALE run); weak scaling is the headline `value`"}
+        if rank == 0:
+            log(f"[strong] {strong}")
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([ms_total, ms_e2e, ms_area, ms_vol, ms_exch, ms_e2e_host], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -550,7 +595,7 @@ def run_ours(args):
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (args.scaling == "strong" and world > 1) else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_string(f, world), "inputs": INPUTS,
                    "partition": ("contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) "
@@ -577,6 +622,8 @@ def run_ours(args):
     }
     if parity is not None:
         line["parity"] = parity
+    if strong is not None:
+        line["strong_scaling"] = strong
     if world == 1 and not args.no_configs:
         # the other single-GPU configs of BASELINE.json, measured in this same run (scripts/bench_configs.py)
         from scripts.bench_configs import run_all
@@ -606,6 +653,9 @@ def main():
     ap.add_argument("--exchange", default="overlap", choices=["overlap", "serial", "nccl"],
                     help="multi-GPU completion of shared rows: peer-memory exchange on a second stream underneath the gradient kernels "
                          "(default), the same exchange serialised behind them, or one ncclAllReduce of the packed rows (comparison)")
+    ap.add_argument("--scaling", default="both", choices=["both", "weak", "strong"],
+                    help="N > 1: the headline line is weak scaling (N x 10M triangles); 'both' adds a strong-scaling leg (the 10M-triangle sphere "
+                         "cut N ways) as `strong_scaling`; 'strong' makes the 10M-triangle sphere the only workload")
     ap.add_argument("--no-fused-push", action="store_true", help="multi-GPU: push the shared rows in the exchange kernel instead of the gradient kernels")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -196,9 +196,11 @@ int mcu_matrix_zero_columns(mcu_matrix *m, int n, const int *host_cols);
 int mcu_mesh_bind_vertices(mcu_mesh *m, mcu_matrix *vert);
 int mcu_eval_matrix(mcu_mesh *m, const mcu_functional *f, mcu_selection *sel, int mode, mcu_matrix *out);
 
-/* ---- Line / area integrals of an integrand over the elements: integrate_integrate (integrate.c:769-800), the default
- *      element integrator behind LineIntegral / AreaIntegral (functional.c:5176-5245, 5354-5428): adaptive Gauss-Kronrod
- *      7/15 on lines, nested Grundmann-Moeller rules with quadrisection on triangles, accuracy goal 1e-6 relative to the
+/* ---- Line / area / volume integrals of an integrand over the elements (grade 1, 2, 3): integrate_integrate
+ *      (integrate.c:769-800), the default element integrator behind LineIntegral / AreaIntegral / VolumeIntegral
+ *      (functional.c:5176-5245, 5354-5428, 5471-5546): adaptive Gauss-Kronrod 7/15 on lines (integrate_lineint), nested
+ *      Grundmann-Moeller rules with quadrisection on triangles (integrate_areaint), the 35/56-point pair with 8-way
+ *      subdivision on tetrahedra (integrate_volint, integrate.c:677-752), accuracy goal 1e-6 relative to the
  *      element's estimate, result multiplied by the element size.  The reference calls a Morpho closure at every node;
  *      here the integrand is a postfix program over the interpolated position (MCU_X_POS a = 0,1,2) and the
  *      interpolated components of the given P1 fields (MCU_X_FIELD a = flattened component index, fields in
@@ -213,15 +215,16 @@ enum {
     MCU_X_CEIL = 25, MCU_X_LOG10 = 26,
     /* element constants, the helper builtins of functional.c:4396-4745: a = component of the unit tangent of a line
      * element / the unit normal of a triangle in 3D; MCU_X_GRADQ a = 3 * (flattened field component) + k is the
-     * derivative along x_k of the P1 interpolant of that component on a triangle (gradsq_evaluategradient) */
+     * derivative along x_k of the P1 interpolant of that component on a triangle (gradsq_evaluategradient) or a
+     * tetrahedron in 3D (gradsq_evaluategradient3d) */
     MCU_X_TANGENT = 27, MCU_X_NORMAL = 28, MCU_X_GRADQ = 29
 };
 typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
 int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                  mcu_selection *sel, int mode, double *host_out);
-/* LineIntegral/AreaIntegral gradient and fieldgradient: central differences over the quadrature, as the reference
+/* LineIntegral/AreaIntegral/VolumeIntegral gradient and fieldgradient: central differences over the quadrature, as the reference
  * (functional_mapnumericalgradient / functional_mapnumericalfieldgradient, functional.c:1142-1247, 1305-1503 with
- * lineintegral_integrand / areaintegral_integrand).  wrt < 0: positions (nv * dim doubles); wrt = k: the k-th field
+ * lineintegral_integrand / areaintegral_integrand / volumeintegral_integrand).  wrt < 0: positions (nv * dim doubles); wrt = k: the k-th field
  * (nv * psize_k doubles, the layout of the Field's store). */
 int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                           mcu_selection *sel, int wrt, double *host_out);

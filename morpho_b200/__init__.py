@@ -6,6 +6,6 @@ the thin host-side mirror of the reference's functional API used by tests and be
 from ._lib import MorphoError, init, lib, set_option  # noqa: F401
 from .geometry import Field, Mesh, Selection  # noqa: F401
 from .functionals import (Area, AreaEnclosed, EquiElement, Functional, GradSq, Length, LineCurvatureSq, Nematic,  # noqa: F401
-                          NematicElectric, NormSq, PairwisePotential, Volume, VolumeEnclosed, LineIntegral, AreaIntegral, ScalarPotential)
+                          NematicElectric, NormSq, PairwisePotential, Volume, VolumeEnclosed, LineIntegral, AreaIntegral, VolumeIntegral, ScalarPotential)
 from . import integrand  # noqa: F401
 from . import meshgen  # noqa: F401

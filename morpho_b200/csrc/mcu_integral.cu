@@ -1,14 +1,18 @@
-// mcu_integral.cu — quadrature of an integrand over line and area elements on the device.
+// mcu_integral.cu — quadrature of an integrand over line, area and volume elements on the device.
 //
 // What it replaces: integrate_integrate (src/geometry/integrate.c:769-800), the reference's default ("old")
-// element integrator behind LineIntegral / AreaIntegral (lineintegral_integrand functional.c:5176-5245,
-// areaintegral_integrand 5354-5428): integrate the integrand over the element in barycentric coordinates with an
-// adaptive nested rule, then multiply by the element size.
+// element integrator behind LineIntegral / AreaIntegral / VolumeIntegral (lineintegral_integrand functional.c:5176-5245,
+// areaintegral_integrand 5354-5428, volumeintegral_integrand 5471-5546): integrate the integrand over the element in
+// barycentric coordinates with an adaptive nested rule, then multiply by the element size.
 //   lines      Gauss 7 / Kronrod 15 pair (integrate.c:38-196): accept when |K15 - G7| * 2^-depth / |global estimate|
 //              < 1e-6, else bisect and average the halves;
 //   triangles  Grundmann-Moeller rules of degree 3, 5, 7 on 4 / 10 / 20 nested points (integrate.c:205-415, "Walkington"):
 //              accept the degree-5 value when it agrees with degree 3, else the degree-7 value when it agrees with
 //              degree 5, else split into four and average.
+//   tetrahedra the 35- and 56-point symmetric rules of Shunn & Ham, J. Comput. Appl. Math. 236, 4348 (2012), which the
+//              reference tabulates (integrate.c:480-577): accept the 56-point value when |R56 - R35| * 8^-depth /
+//              |global estimate| < 1e-6, else split into the reference's eight sub-tetrahedra (integrate.c:662-669) and
+//              average (integrate_volint, integrate.c:677-752).
 // In the reference the integrand is a Morpho closure called through the VM at every node.  A closure cannot
 // run on the device; here the integrand is a small postfix PROGRAM (mcu_expr_op, include/morpho_cuda.h) over the
 // interpolated position and the interpolated components of P1 fields — what a closure→device translator
@@ -36,12 +40,17 @@ extern long g_mcu_launches;
 #define MI_STACK 24       // expression stack
 #define MI_MAXDEPTH_LINE 30
 #define MI_MAXDEPTH_TRI 10
+#define MI_MAXDEPTH_TET 5   // the reference recurses without a limit here; 8^5 leaves of 91 nodes bound a thread's work
+#define MI_TET_A 35
+#define MI_TET_B 56
 #define MI_GOAL 1e-6      // INTEGRATE_ACCURACYGOAL (integrate.h:22)
 
 struct MiRules {
     double gk_t[15], gk_wg[15], gk_wk[15];     // line nodes in [0,1] and the two weight sets (Gauss weights 0 beyond 7)
     double tri[20][3];                         // triangle nodes (barycentric)
     double w1[2], w2[3], w3[4];                // weights per group: centroid, degree-3 ring, degree-5 ring, degree-7 ring
+    double tet[MI_TET_A + MI_TET_B][4];        // tetrahedron nodes (barycentric): the 35-point rule, then the 56-point rule
+    double tetw[MI_TET_A + MI_TET_B];
 };
 __constant__ MiRules c_rules;
 __constant__ mcu_expr_op c_prog[MI_MAXOPS];
@@ -200,6 +209,46 @@ __device__ double mi_tri(const MiView &v, const double (*xv)[3], const double (*
     return sum;
 }
 
+// integrate_volint (integrate.c:677-752).  A sub-tetrahedron = four corners in the barycentric coordinates of the root.
+// Children (integrate.c:662-669) of corners 0..3 and edge midpoints 4 = 01, 5 = 02, 6 = 03, 7 = 12, 8 = 13, 9 = 23.
+__constant__ unsigned char c_tetsub[8][4] = {{1, 4, 7, 8}, {0, 4, 7, 9}, {0, 4, 8, 9}, {4, 7, 8, 9}, {0, 5, 7, 9}, {0, 6, 8, 9}, {2, 5, 7, 9}, {3, 6, 8, 9}};
+
+__device__ double mi_tet(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
+    double sb[7 * MI_MAXDEPTH_TET + 2][16];
+    int sd[7 * MI_MAXDEPTH_TET + 2];
+    int top = 0;
+    for (int i = 0; i < 16; i++) sb[0][i] = (i % 5 == 0) ? 1.0 : 0.0;
+    sd[0] = 0; top = 1;
+    double sum = 0.0, gest = 0.0;
+    while (top > 0) {
+        top--;
+        const int d = sd[top];
+        double B[10][4];
+        for (int j = 0; j < 4; j++) for (int k = 0; k < 4; k++) B[j][k] = sb[top][4 * j + k];
+        const double af = ldexp(1.0, -3 * d);
+        double r1 = 0.0, r2 = 0.0;
+        for (int i = 0; i < MI_TET_A + MI_TET_B; i++) {
+            double lam[4];
+            for (int k = 0; k < 4; k++)
+                lam[k] = c_rules.tet[i][0] * B[0][k] + c_rules.tet[i][1] * B[1][k] + c_rules.tet[i][2] * B[2][k] + c_rules.tet[i][3] * B[3][k];
+            const double f = mi_at<4>(v, xv, qv, lam);
+            if (i < MI_TET_A) r1 += c_rules.tetw[i] * f;
+            else r2 += c_rules.tetw[i] * f;
+        }
+        if (d == 0) gest = fabs(r2);
+        double eps = (r2 - r1) * af;
+        if (gest > MCU_EPS) eps /= gest;
+        if (fabs(eps) < MI_GOAL || d >= MI_MAXDEPTH_TET) { sum += r2 * af; continue; }
+        const int pair[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+        for (int m = 0; m < 6; m++) for (int k = 0; k < 4; k++) B[4 + m][k] = 0.5 * (B[pair[m][0]][k] + B[pair[m][1]][k]);
+        for (int c = 7; c >= 0; c--) {                         // pushed in reverse: visited in the reference's order
+            for (int j = 0; j < 4; j++) for (int k = 0; k < 4; k++) sb[top][4 * j + k] = B[c_tetsub[c][j]][k];
+            sd[top] = d + 1; top++;
+        }
+    }
+    return sum;
+}
+
 // tangent() / normal() / grad(q) of the element (integral_evaluatetangent, integral_evaluatenormal,
 // integral_evaluategradient → gradsq_evaluategradient; functional.c:4402-4425, 4444-4470, 4716-4726)
 __device__ __forceinline__ void mi_derive(const MiView &v, const double (*xv)[3], double (*qv)[MI_MAXQ]) {
@@ -217,8 +266,9 @@ __device__ __forceinline__ void mi_derive(const MiView &v, const double (*xv)[3]
         for (int k = 0; k < nv; k++) for (int j = 0; j < 3; j++) qv[k][v.tn_slot + j] = t[j];
     }
     for (int i = 0; i < v.ngrad; i++) {
-        double vals[3] = {qv[0][v.gsrc[i]], qv[1][v.gsrc[i]], qv[2][v.gsrc[i]]}, gr[3] = {0.0, 0.0, 0.0};
-        p1grad_tri(v.dim, xv, 1, vals, 1, gr);
+        double vals[4] = {qv[0][v.gsrc[i]], qv[1][v.gsrc[i]], qv[2][v.gsrc[i]], v.g == 3 ? qv[3][v.gsrc[i]] : 0.0}, gr[3] = {0.0, 0.0, 0.0};
+        if (v.g == 3) p1grad_tet(xv, 1, vals, 1, gr);          // gradsq_evaluategradient3d (functional.c:3584-3620)
+        else p1grad_tri(v.dim, xv, 1, vals, 1, gr);
         for (int k = 0; k < nv; k++) for (int j = 0; j < 3; j++) qv[k][v.gslot[i] + j] = gr[j];
     }
 }
@@ -231,9 +281,12 @@ __device__ __forceinline__ double mi_element(const MiView &v, const double (*xv)
         val = mi_line(v, xv, qv);
         double s[3] = {xv[1][0] - xv[0][0], xv[1][1] - xv[0][1], xv[1][2] - xv[0][2]};
         size = sqrt(dot3(s, s));
-    } else {
+    } else if (v.g == 2) {
         val = mi_tri(v, xv, qv);
         size = area_of(xv);
+    } else {
+        val = mi_tet(v, xv, qv);
+        size = volume_of(xv);
     }
     return val * size;
 }
@@ -251,7 +304,7 @@ __global__ void __launch_bounds__(128) k_integral(MiView v, double *out) {
     int ce = blockIdx.x * 128 + threadIdx.x;
     if (ce >= v.n) return;
     const int e = v.eids ? v.eids[ce] : ce;
-    double xv[3][3], qv[3][MI_MAXQ];
+    double xv[4][3], qv[4][MI_MAXQ];
     mi_gather(v, e, xv, qv);
     out[e] = mi_element(v, xv, qv);
 }
@@ -267,7 +320,7 @@ __global__ void __launch_bounds__(128) k_integral_fd(MiView v, int qbase, int nc
     if (t >= (long) v.n * nv) return;
     const int ce = (int) (t / nv), corner = (int) (t - (long) ce * nv);
     const int e = v.eids ? v.eids[ce] : ce;
-    double xv[3][3], qv[3][MI_MAXQ];
+    double xv[4][3], qv[4][MI_MAXQ];
     mi_gather(v, e, xv, qv);
     for (int c = 0; c < ncomp; c++) {
         double *slot = qbase < 0 ? &xv[corner][c] : &qv[corner][qbase + c];
@@ -349,12 +402,42 @@ static void make_rules(MiRules &R) {
     node(7, 1, 1, 9); node(1, 7, 1, 9); node(1, 1, 7, 9);
     node(3, 5, 1, 9); node(3, 1, 5, 9); node(5, 3, 1, 9); node(5, 1, 3, 9); node(1, 3, 5, 9); node(1, 5, 3, 9);
     node(3, 3, 3, 9);
+    // Tetrahedron: the 35- and 56-point rules of Shunn & Ham (2012) as the reference tabulates them (integrate.c:480-577),
+    // stored here by symmetry orbit: generator values a, b, c, the weight, and the reference's order of the
+    // permutations inside the orbit (it fixes only the order of the weighted sums).
+    struct Orbit { const char *perms; double a, b, c, w; };
+    static const char *P4 = "abbb babb bbab bbba", *P1 = "aaaa", *P6 = "aacc acac acca caac caca ccaa";
+    static const char *P12A = "abcc bacc acbc bcac accb bcca cabc cbac cacb cbca ccab ccba";
+    static const char *P12B = "abbc babc bbac abcb bacb bbca acbb bcab bcba cabb cbab cbba";
+    static const Orbit rule35[] = {
+        {P4, 0.9197896733368800, 0.0267367755543735, 0.0, 0.0021900463965388},
+        {P12A, 0.1740356302468940, 0.7477598884818090, 0.0391022406356488, 0.0143395670177665},
+        {P6, 0.4547545999844830, 0.0, 0.0452454000155172, 0.0250305395686746},
+        {P12B, 0.5031186450145980, 0.2232010379623150, 0.0504792790607720, 0.0479839333057554},
+        {P1, 0.2500000000000000, 0.0, 0.0, 0.0931745731195340}};
+    static const Orbit rule56[] = {
+        {P4, 0.9551438045408220, 0.0149520651530592, 0.0, 0.0010373112336140},
+        {P12A, 0.7799760084415400, 0.1518319491659370, 0.0340960211962615, 0.0096016645399480},
+        {P12A, 0.3549340560639790, 0.5526556431060170, 0.0462051504150017, 0.0164493976798232},
+        {P12B, 0.5381043228880020, 0.2281904610687610, 0.0055147549744775, 0.0153747766513310},
+        {P12B, 0.1961837595745600, 0.3523052600879940, 0.0992057202494530, 0.0293520118375230},
+        {P4, 0.5965649956210170, 0.1344783347929940, 0.0, 0.0366291366405108}};
+    int t = 0;
+    auto expand = [&](const Orbit *o, int norb) {
+        for (int k = 0; k < norb; k++)
+            for (const char *q = o[k].perms; *q; q += (q[4] ? 5 : 4)) {
+                for (int j = 0; j < 4; j++) R.tet[t][j] = q[j] == 'a' ? o[k].a : (q[j] == 'b' ? o[k].b : o[k].c);
+                R.tetw[t++] = o[k].w;
+            }
+    };
+    expand(rule35, 5);
+    expand(rule56, 6);
 }
 
 // arguments shared by mcu_integral and mcu_integral_gradient: validates, uploads the rules and the program, fills the view
 static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                           mcu_selection *sel, MiView &v, cudaStream_t st) {
-    if (!m || (grade != 1 && grade != 2) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
+    if (!m || (grade < 1 || grade > 3) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
     if (!m->conn[grade].present) { mcu_set_error("mesh has no elements of grade %d", grade); return MCU_ERR_ELNOTFOUND; }
     if (sel && (sel->m != m || sel->g != grade)) { mcu_set_error("selection does not belong to this mesh / grade"); return MCU_ERR_ARGS; }
     static bool rules_up = false;
@@ -394,7 +477,7 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
             op.op = MCU_X_FIELD; op.a = v.tn_slot + op.a;
         } else if (op.op == MCU_X_GRADQ) {
             const int comp = op.a / 3, k = op.a % 3;
-            if (grade != 2 || op.a < 0 || comp >= v.nq_in || k >= m->dim) { mcu_set_error("grad() needs a triangle and a field component"); return MCU_ERR_UNSUPPORTED; }
+            if ((grade != 2 && !(grade == 3 && m->dim == 3)) || op.a < 0 || comp >= v.nq_in || k >= m->dim) { mcu_set_error("grad() needs a triangle or a tetrahedron and a field component"); return MCU_ERR_UNSUPPORTED; }
             int gi = -1;
             for (int j = 0; j < v.ngrad; j++) if (v.gsrc[j] == comp) gi = j;
             if (gi < 0) {

@@ -611,7 +611,7 @@ MC_EVENEER(total, MCU_TOTAL)
 MC_EVENEER(integrand, MCU_INTEGRAND)
 MC_EVENEER(gradient, MCU_GRADIENT)
 
-/* LineIntegral / AreaIntegral, total and integrand (functional.c:5186-5243, 5371-5426).  The integrand closure is
+/* LineIntegral / AreaIntegral / VolumeIntegral (functional.c:5186-5243, 5371-5426, 5471-5546).  The integrand closure is
  * translated into a postfix program (mc_translate.h); what cannot be translated — and method dictionaries, reference
  * meshes, fields on finite-element spaces — goes to the reference builtin. */
 #define MC_MAXPROG 256
@@ -790,6 +790,10 @@ MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, total, MCU_TOTAL)
 MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, integrand, MCU_INTEGRAND)
 MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, gradient, MCU_GRADIENT)
 MC_IVENEER(AreaIntegral, MESH_GRADE_AREA, fieldgradient, MCU_FIELDGRADIENT)
+MC_IVENEER(VolumeIntegral, MESH_GRADE_VOLUME, total, MCU_TOTAL)
+MC_IVENEER(VolumeIntegral, MESH_GRADE_VOLUME, integrand, MCU_INTEGRAND)
+MC_IVENEER(VolumeIntegral, MESH_GRADE_VOLUME, gradient, MCU_GRADIENT)
+MC_IVENEER(VolumeIntegral, MESH_GRADE_VOLUME, fieldgradient, MCU_FIELDGRADIENT)
 
 #define MC_VENEER(cls, FID, GRADE, meth, MODE) \
     static builtinfunction orig_##cls##_##meth = NULL; \
@@ -1134,6 +1138,7 @@ static void mc_core_initialize(void) {
     PATCH(ScalarPotential, total); PATCH(ScalarPotential, integrand); PATCH(ScalarPotential, gradient);
     PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
     PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
+    PATCH(VolumeIntegral, total); PATCH(VolumeIntegral, integrand); PATCH(VolumeIntegral, gradient); PATCH(VolumeIntegral, fieldgradient);
 
     object probe;
     memset(&probe, 0, sizeof(probe));

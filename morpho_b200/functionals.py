@@ -20,7 +20,7 @@ from ._lib import (MCU_FIELDGRADIENT, MCU_GRADIENT, MCU_INTEGRAND, MCU_TOTAL, FU
 from .geometry import Field, Mesh, Selection
 
 __all__ = ["Functional", "Length", "AreaEnclosed", "Area", "VolumeEnclosed", "Volume", "LineCurvatureSq", "EquiElement",
-           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral", "ScalarPotential"]
+           "GradSq", "NormSq", "Nematic", "NematicElectric", "PairwisePotential", "LineIntegral", "AreaIntegral", "VolumeIntegral", "ScalarPotential"]
 
 
 class Functional:
@@ -329,6 +329,11 @@ class LineIntegral(_Integral):
 
 class AreaIntegral(_Integral):
     grade = 2
+
+
+class VolumeIntegral(_Integral):
+    """functional.c:5471-5576; integrate_volint (integrate.c:677-752) on the device."""
+    grade = 3
 
 
 class ScalarPotential:

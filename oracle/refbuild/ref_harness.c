@@ -412,7 +412,9 @@ long refh_integral(void *mesh, int g, int nops, const refh_expr_op *prog, int nq
         }
         double size, val;
         if (!functional_elementsize(hvm, m, g, e, nv, vid, &size)) return -1;
-        if (!integrate_integrate(refh_integrand, m->dim, (unsigned) g, x, (unsigned) nq, nq ? q : NULL, &pr, &val)) {
+        /* integrate_volint builds its table of sub-element quantities from quantity[0..3] even when there are none
+         * (integrate.c:707): the VM always hands it four lists, so does this harness */
+        if (!integrate_integrate(refh_integrand, m->dim, (unsigned) g, x, (unsigned) nq, (nq || g == 3) ? q : NULL, &pr, &val)) {
             snprintf(lasterr, sizeof(lasterr), "integrate_integrate failed on element %d", e);
             return -1;
         }

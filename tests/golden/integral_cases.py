@@ -1,4 +1,4 @@
-"""Seeded cases for LineIntegral / AreaIntegral: each integrand is written twice, as a Python callable for the
+"""Seeded cases for LineIntegral / AreaIntegral / VolumeIntegral: each integrand is written twice, as a Python callable for the
 device path (recorded by morpho_b200.integrand.trace) and as the Morpho closure the unmodified VM runs when the
 golden file is made.  Fields are polynomials of the vertex position so that both sides build the same values."""
 import numpy as np
@@ -31,10 +31,28 @@ def meshes():
     out["disk2d"] = (v, {1: mg.edges_from_faces(c), 2: c})
     v, e = mg.polyline_loop(24, 3, 11, 0.1)
     out["loop"] = (v, {1: e})
+    v, t = mg.tet_cube(2)
+    rng = np.random.Generator(np.random.PCG64(17))
+    v = v + 0.05 * rng.uniform(-1, 1, size=v.shape)
+    out["tets"] = (v, {3: t})
     return out
 
 
 # name, mesh, grade, python callable, morpho closure, fields, selection ids or None
+VOLUME_CASES = [
+    ("vol_const", "tets", 3, lambda x: 1.0 + 0 * x[0], "fn (x) 1+0*x[0]", [], None),
+    ("vol_poly", "tets", 3, lambda x: x[0] * x[1] * x[2] + x[2] ** 3 - 0.5 * x[0] ** 2, "fn (x) x[0]*x[1]*x[2]+x[2]^3-0.5*x[0]^2", [], None),
+    ("vol_osc", "tets", 3, lambda x: exp(x[0]) * cos(5 * x[1]) + sin(4 * x[2]) ** 2, "fn (x) exp(x[0])*cos(5*x[1])+sin(4*x[2])^2", [], None),
+    ("vol_peak", "tets", 3, lambda x: 1.0 / (0.01 + (x[0] - 0.3) ** 2 + (x[1] - 0.6) ** 2 + x[2] ** 2),
+     "fn (x) 1/(0.01+(x[0]-0.3)^2+(x[1]-0.6)^2+x[2]^2)", [], None),
+    ("vol_field", "tets", 3, lambda x, p, q: p * p + q[0] * q[1] - q[2] * x[2], "fn (x, p, q) p*p+q[0]*q[1]-q[2]*x[2]", ["phi", "q"], None),
+    ("vol_sel", "tets", 3, lambda x, q: sqrt(1.0 + q[1]) * exp(-x[2]), "fn (x, q) sqrt(1+q[1])*exp(-x[2])", ["q"], [0, 5, 6, 17, 30, 47]),
+    ("vol_gradsq", "tets", 3, lambda x, p: grad(p)[0] ** 2 + grad(p)[1] ** 2 + grad(p)[2] ** 2 + p * grad(p)[2],
+     "fn (x, p) grad(p).inner(grad(p))+p*grad(p)[2]", ["phi"], None),
+    ("vol_gradvec", "tets", 3, lambda x, q: sum(grad(q)[k][c] ** 2 for k in range(3) for c in range(3)) + grad(q)[2][1] * q[0],
+     "fn (x, q) { var g = grad(q); return g[0].inner(g[0])+g[1].inner(g[1])+g[2].inner(g[2])+g[2][1]*q[0] }", ["q"], None),
+]
+
 CASES = [
     ("line_poly", "loop", 1, lambda x: x[0] ** 2 * x[1] + 1.0, "fn (x) x[0]^2*x[1]+1", [], None),
     ("line_osc", "loop", 1, lambda x: sin(9 * x[0]) * exp(x[1]) + cos(7 * x[2]), "fn (x) sin(9*x[0])*exp(x[1])+cos(7*x[2])", [], None),
@@ -57,7 +75,7 @@ CASES = [
      "fn (x, p) grad(p).inner(grad(p))+p*grad(p)[0]", ["phi"], None),
     ("area_gradvec", "sphere", 2, lambda x, q: sum(grad(q)[k][c] ** 2 for k in range(3) for c in range(3)) + grad(q)[1][0] * q[2],
      "fn (x, q) { var g = grad(q); return g[0].inner(g[0])+g[1].inner(g[1])+g[2].inner(g[2])+g[1][0]*q[2] }", ["q"], None),
-]
+] + VOLUME_CASES
 
 
 def fields_for(vert):
@@ -69,7 +87,9 @@ def fields_for(vert):
 GRAD_CASES = [("line_poly", -1), ("line_osc", -1), ("line_field", -1), ("line_field", 0), ("line_field", 1), ("line_sel", -1),
               ("area_quad", -1), ("area_osc", -1), ("area_field", -1), ("area_field", 0), ("area_field", 1), ("area_sel", 0),
               ("line_tangent", -1), ("area_anchor", -1), ("area_anchor", 0), ("area_gradsq", -1), ("area_gradsq", 0),
-              ("area_gradvec", 0)]
+              ("area_gradvec", 0),
+              ("vol_poly", -1), ("vol_osc", -1), ("vol_field", -1), ("vol_field", 0), ("vol_field", 1), ("vol_sel", 0), ("vol_gradsq", -1),
+              ("vol_gradsq", 0)]
 
 
 # ScalarPotential: name, mesh, f, gradf or None, Morpho sources, selected vertex ids or None

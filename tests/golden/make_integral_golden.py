@@ -37,7 +37,7 @@ def vm_integrands(tmp, ms):
         for fname, fsrc in FIELD_SRC[v.shape[1]].items():
             src.append(f"var {fname}_{name} = Field(m_{name}, {fsrc})")
     for name, mesh, grade, _, closure, flds, sel in CASES:
-        cls = "LineIntegral" if grade == 1 else "AreaIntegral"
+        cls = {1: "LineIntegral", 2: "AreaIntegral", 3: "VolumeIntegral"}[grade]
         fargs = "".join(f", {f}_{mesh}" for f in flds)
         src.append(f"var r_{name} = {cls}({closure}{fargs}).integrand(m_{mesh})")
         src.append(f'print "@{name}"')
@@ -45,7 +45,7 @@ def vm_integrands(tmp, ms):
     bycase = {c[0]: c for c in CASES}
     for gname, wrt in GRAD_CASES:
         name, mesh, grade, _, closure, flds, sel = bycase[gname]
-        cls = "LineIntegral" if grade == 1 else "AreaIntegral"
+        cls = {1: "LineIntegral", 2: "AreaIntegral", 3: "VolumeIntegral"}[grade]
         fargs = "".join(f", {f}_{mesh}" for f in flds)
         key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
         selarg = ""

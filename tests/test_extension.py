@@ -153,6 +153,21 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_volume_integral_closures_run_on_the_gpu(tmp_path):
+    """VolumeIntegral (functional.c:5471-5576) with the default integrator integrate_volint (integrate.c:677-752) on a
+    162-tetrahedron lattice: totals / integrands at 1e-12, finite-difference gradients at the FD tolerance; no fallbacks."""
+    src = script("volume_integrals.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    stats = [int(v) for v in NUM.findall(new[-1])]
+    evals, fallbacks, translated = stats[0], stats[3], stats[5]
+    assert translated == 32 and fallbacks == 0, (stats, err)      # 18 values + 14 gradients
+    cut = ref.index("-- gradients")
+    compare(ref[:cut], new[:cut], 1e-12)
+    compare(ref[cut:], new[cut:-1], 2e-9)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,tol", [("functionals_basic.morpho", 1e-12), ("catenoid_cg.morpho", 1e-12),
                                       ("volume_constraint.morpho", 1e-11), ("field_functionals.morpho", 1e-9)])
 def test_scripts_agree_with_the_stock_reference(tmp_path, name, tol):

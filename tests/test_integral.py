@@ -1,4 +1,4 @@
-"""LineIntegral / AreaIntegral: the device quadrature (morpho_b200/csrc/mcu_integral.cu) against golden vectors made
+"""LineIntegral / AreaIntegral / VolumeIntegral: the device quadrature (morpho_b200/csrc/mcu_integral.cu) against golden vectors made
 by the unmodified reference running real closures in its VM (tests/golden/make_integral_golden.py), and against the
 reference's own integrate_integrate called live through the harness where oracle/_ref is present.
 
@@ -84,9 +84,9 @@ def _device(mb, case, ms):
     name, mesh, grade, fn, _, flds, sel = case
     v, gr = ms[mesh]
     fd = fields_for(v)
-    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2))
+    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2), volumes=gr.get(3))
     fl = [mb.Field(m, fd[f]) for f in flds]
-    cls = mb.LineIntegral if grade == 1 else mb.AreaIntegral
+    cls = {1: mb.LineIntegral, 2: mb.AreaIntegral, 3: mb.VolumeIntegral}[grade]
     args = [m] + ([mb.Selection(m, ids={grade: sel})] if sel is not None else [])
     func = cls(fn, *fl)
     return func.integrand(*args), func.total(*args)
@@ -126,9 +126,9 @@ def test_device_integral_gradients_match_vm_goldens(mb, gcase):
     gold = np.load(GOLD)[f"grad__{gname}__{'x' if wrt < 0 else wrt}"]
     v, gr = meshes()[mesh]
     fd = fields_for(v)
-    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2))
+    m = mb.Mesh(v, edges=gr.get(1), faces=gr.get(2), volumes=gr.get(3))
     fl = [mb.Field(m, fd[f]) for f in flds]
-    func = (mb.LineIntegral if grade == 1 else mb.AreaIntegral)(fn, *fl)
+    func = {1: mb.LineIntegral, 2: mb.AreaIntegral, 3: mb.VolumeIntegral}[grade](fn, *fl)
     args = [m] + ([mb.Selection(m, ids={grade: sel})] if sel is not None else [])
     got = func.gradient(*args) if wrt < 0 else func.fieldgradient(fl[wrt], *args[1:])
     assert got.size == gold.size
