@@ -341,10 +341,10 @@ def run_ours(args):
         if world > 1:
             from morpho_b200.partition import PeerExchange
             exch = PeerExchange(part, torch, dist, ngrad=2)   # NVLink peer memory, one kernel per exchange, no collective call
-            if not args.no_fused_push and args.exchange != "nccl":
+            if args.fused_push and args.exchange != "nccl":
                 exch.attach(mesh)                             # the gradient kernels store the shared rows into the peers' buffers themselves
 
-        fused = exch is not None and not args.no_fused_push and args.exchange != "nccl"
+        fused = exch is not None and args.fused_push and args.exchange != "nccl"
 
         nccl_state = {}
 
@@ -387,6 +387,15 @@ def run_ours(args):
         return SimpleNamespace(f=f, part=part, vert=vert, conn=conn, nel_local=nel_local, nel_global=nel_global, mesh=mesh, area=area, vol=vol,
                                nout=nout, g_area=g_area, g_vol=g_vol, exch=exch, fused=fused, step_device=step_device)
 
+    t_run = time.time()
+    if world > 1:
+        # a rank that waits for a peer that never arrives must not hang the box: end the process group loudly instead
+        def _watchdog():
+            log(f"[rank {rank}] bench.py watchdog: no result after {args.watchdog} s, giving up")
+            os._exit(4)
+        wd = threading.Timer(float(args.watchdog), _watchdog)
+        wd.daemon = True
+        wd.start()
     f = frequency_for(world, args.freq) if args.scaling != "strong" else args.freq
     W = build_workload(f)
     part, vert, conn, nel_local, nel_global, mesh, area, vol = W.part, W.vert, W.conn, W.nel_local, W.nel_global, W.mesh, W.area, W.vol
@@ -397,6 +406,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def phase(name):
+        if world > 1 and rank == 0:
+            log(f"[phase +{time.time() - t_run:.1f}s] {name}")
+
+    def first_step(w_):
+        """One step, then the exchange's status word: a peer that never arrives must end the run with a message (and the
+        library's dump of flags and epochs), not as a wrong parity figure or a hang."""
+        if w_.exch is None:
+            return
+        w_.step_device()
+        barrier()
+        if w_.exch.status() != 0:
+            raise RuntimeError("halo exchange: a peer did not arrive in time in the first step")
+
+    first_step(W)
     # ---- parity of what is about to be timed (checker only: the CPU oracle, never the thing measured) ------
     parity = None
     if not args.no_parity:
@@ -407,6 +431,7 @@ def run_ours(args):
             raise SystemExit(f"parity check failed: {parity}")
 
     # ---- device-resident timing -------------------------------------------------------------
+    phase("warm-up")
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -418,9 +443,13 @@ def run_ours(args):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    phase("timed steps")
     e_start.record(stream)
+    sync_every = int(os.environ.get("BENCH_SYNC_EVERY", "0"))         # diagnostics only
     for k in range(args.steps):
         step_device(ev[k])
+        if sync_every and (k + 1) % sync_every == 0:
+            stream.synchronize()
     e_end.record(stream)
     barrier()
     launches = L.mcu_launch_count() - launches0
@@ -431,6 +460,7 @@ def run_ours(args):
     # nvidia-smi cannot sample faster than ~100 ms: when the timed region is shorter than that, keep the SAME
     # load running (untimed) until a few samples exist, so the clocks line describes the kernels under load
     # (every rank runs the same number of steps: the shared-vertex exchange pairs up launches across ranks)
+    phase("clock samples under load")
     t_load = time.time()
     for _ in range(60):
         for _ in range(50):
@@ -479,9 +509,11 @@ def run_ours(args):
         return a.elapsed_time(b) / nsteps
 
     e2e_steps = 1 if args.quick else max(3, min(args.steps, 10))
+    phase("end to end, host buffers")
     ms_e2e_host = timed(step_e2e_host, e2e_steps, 0 if args.quick else 2)
     checksum = float(ha[:3].sum() + hg[:3].sum())
 
+    phase("end to end, device-resident line-search step")
     dim = vert.shape[1]
     X = L.mcu_matrix_create(dim, vert.shape[0])
     F = L.mcu_matrix_create(dim, vert.shape[0])
@@ -532,7 +564,9 @@ def run_ours(args):
     # ---- strong scaling (N > 1): the SAME 10M-triangle sphere of BASELINE config 2 cut N ways ----------------
     strong = None
     if world > 1 and args.scaling == "both":
+        phase("strong scaling")
         S = build_workload(args.freq)
+        first_step(S)
         par_s = None
         if not args.no_parity:
             par_s = parity_check(S.part, S.vert, S.conn, S.step_device, S.g_area, S.g_vol, torch, dist, world, rank, barrier)
@@ -562,6 +596,24 @@ def run_ours(args):
                   "note": "total work fixed: compare `value` with the N=1 line's (the driver's SCALE run); weak scaling is the headline `value`"}
         if rank == 0:
             log(f"[strong] {strong}")
+    # ---- BASELINE config 5 partitioned over the N GPUs (N > 1; scripts/bench_configs.py) ------------------
+    config5_multi = None
+    if world > 1 and not args.no_configs:
+        from scripts.bench_configs import config5_partitioned
+        phase("config 5 partitioned")
+        for w_ in (W, locals().get("S")):
+            if w_ is not None:                          # release the sphere workloads first
+                if w_.exch is not None:
+                    w_.exch.close()
+                w_.mesh = w_.g_area = w_.g_vol = None
+        mesh = g_area = g_vol = None
+        torch.cuda.empty_cache()
+        t5 = time.time()
+        config5_multi = config5_partitioned(mb, torch, dist, measured_peak()[0], n=args.tets, log=log)
+        config5_multi["wall_s"] = time.time() - t5
+        if rank == 0:
+            log(f"[configs] 5 partitioned: {config5_multi}")
+
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([ms_total, ms_e2e, ms_area, ms_vol, ms_exch, ms_e2e_host], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -599,7 +651,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": workload_string(f, world), "inputs": INPUTS,
                    "partition": ("contiguous element ranges per GPU; rows of shared vertices pushed into the peers' receive buffers over NVLink (CUDA IPC) "
-                                 f"and summed in rank order; exchange mode: {args.exchange}") if world > 1 else "single GPU",
+                                 f"and summed in rank order; exchange mode: {args.exchange}, pushed by the {'gradient' if args.fused_push else 'exchange'} kernels") if world > 1 else "single GPU",
                    "gradient_path": "persistent patch kernel: bulk-async (TMA) staging of vertex runs into a 3-stage shared-memory ring, one consumer thread per owned vertex walks its ring (owner computes, no atomics)",
                    "kernel_ms": {"area_gradient": ms_area, "volumeenclosed_gradient": ms_vol, "shared_row_exchange": ms_exch if world > 1 else 0.0}},
         "clocks": clocks,
@@ -624,6 +676,8 @@ def run_ours(args):
         line["parity"] = parity
     if strong is not None:
         line["strong_scaling"] = strong
+    if config5_multi is not None:
+        line["configs"] = {"5": config5_multi}
     if world == 1 and not args.no_configs:
         # the other single-GPU configs of BASELINE.json, measured in this same run (scripts/bench_configs.py)
         from scripts.bench_configs import run_all
@@ -647,6 +701,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the gradients before timing")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3/4/5 (N=1 only)")
+    ap.add_argument("--watchdog", type=int, default=1500, help="N > 1: seconds after which a run that has not finished kills itself")
+    ap.add_argument("--tets", type=int, default=204, help="N > 1: cells per edge of the config-5 tetrahedral cube (204 = BASELINE config 5)")
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")
@@ -656,7 +712,11 @@ def main():
     ap.add_argument("--scaling", default="both", choices=["both", "weak", "strong"],
                     help="N > 1: the headline line is weak scaling (N x 10M triangles); 'both' adds a strong-scaling leg (the 10M-triangle sphere "
                          "cut N ways) as `strong_scaling`; 'strong' makes the 10M-triangle sphere the only workload")
-    ap.add_argument("--no-fused-push", action="store_true", help="multi-GPU: push the shared rows in the exchange kernel instead of the gradient kernels")
+    ap.add_argument("--fused-push", action="store_true",
+                    help="multi-GPU, experimental: the gradient kernels store the shared rows into the peers' buffers themselves and raise the flags "
+                         "(default: the exchange kernel pushes them).  Off by default: at 10M triangles per GPU the pushing instantiation of the "
+                         "VolumeEnclosed kernel stalled after 20-50 launches (scripts/halo_watch.py), not root-caused")
+    ap.add_argument("--no-fused-push", action="store_true", help="accepted for compatibility (this is the default now)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

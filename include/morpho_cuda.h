@@ -120,6 +120,7 @@ int mcu_mesh_set_vertices_device(mcu_mesh *m, const double *dev_vert); /* D2D */
 int mcu_mesh_get_vertices(mcu_mesh *m, double *host_vert);            /* D2H */
 double *mcu_mesh_vertices_device(mcu_mesh *m);                        /* device pointer of the mirror */
 int mcu_mesh_set_connectivity(mcu_mesh *m, int grade, int nel, const int *host_rix);
+int mcu_mesh_drop_connectivity(mcu_mesh *m, int grade);                /* Mesh.removegrade (mesh_removegrade, mesh.c:489-498) */
 int mcu_mesh_counts(const mcu_mesh *m, int *dim, int *nv, int nel[4]);
 /* Mesh.addgrade (mesh_addgrade, mesh.c:419-489): elements of grade g (1 or 2) from the next higher grade present, ids in
  * the reference's order of first discovery; built on the device (sort + scan).  mcu_mesh_get_connectivity copies the

@@ -71,6 +71,7 @@ def lib():
         "mcu_mesh_vertices_device": (vp, [vp]),
         "mcu_mesh_set_connectivity": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "mcu_mesh_counts": (C.c_int, [vp, ip, ip, ip]),
+        "mcu_mesh_drop_connectivity": (C.c_int, [vp, C.c_int]),
         "mcu_mesh_addgrade": (C.c_int, [vp, C.c_int, ip]),
         "mcu_mesh_boundary": (C.c_int, [vp, ip, ip, vp, C.c_int]),
         "mcu_integral": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp]),

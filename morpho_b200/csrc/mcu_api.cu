@@ -254,6 +254,15 @@ int mcu_mesh_set_connectivity(mcu_mesh *m, int g, int nel, const int *rix) {
     return MCU_OK;
 }
 
+int mcu_mesh_drop_connectivity(mcu_mesh *m, int g) {
+    if (!m || g < 1 || g > 3) { mcu_set_error("bad connectivity arguments"); return MCU_ERR_ARGS; }
+    if (!m->conn[g].present) return MCU_OK;
+    CK(cudaStreamSynchronize(g_stream));
+    conn_free(m, m->conn[g]);
+    m->conn_version++;
+    return MCU_OK;
+}
+
 int mcu_mesh_counts(const mcu_mesh *m, int *dim, int *nv, int nel[4]) {
     if (!m) return MCU_ERR_ARGS;
     if (dim) *dim = m->dim;

@@ -68,6 +68,8 @@ extern "C" int mcu_halo_join(mcu_halo *h);
 static int halo_join_slot(mcu_halo *h, int slot);
 
 #define HALO_WARPS_MAX 296           // single-warp CTAs: two per SM
+#define HALO_WARPS_SIDE 32           // ... on the second stream, beside the next gradient kernel
+#define HALO_WARPS_OVERTAKING 48     // ... when the launch can get in front of the kernel whose rows it waits for (see halo_slot_launch)
 
 // One launch per (exchange, slot).  Single-warp CTAs.
 __global__ void __maxnreg__(32)
@@ -221,7 +223,21 @@ static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cu
     }
     const int work = std::max(pushed ? 0 : h->n_pairs, h->n_shared * dim);
     int nb = (work + 31) / 32;
-    nb = nb < 1 ? 1 : (nb > HALO_WARPS_MAX ? HALO_WARPS_MAX : nb);
+    // A launch that may OVERTAKE the gradient kernel it waits for (fused pushes, second stream) must leave most SMs
+    // alone: its CTAs spin until the gradient kernel has written the own rows, and an SM that hosts a spinning CTA
+    // cannot take a CTA of the patch kernel when the two kernels ask for different shared-memory carve-outs (the
+    // patch kernel needs the largest one) — with a spinning CTA on every SM the gradient kernel never starts and both
+    // sit there until the time-out (seen at N = 2 with >= 1500 shared vertices: 199-296 CTAs on 148 SMs).
+    // On the second stream the launch shares the SMs with the next gradient kernel, whose persistent CTAs want all of an
+    // SM's shared memory: every SM that hosts one of these warps runs that kernel with one CTA instead of two until the
+    // warp is gone (VolumeEnclosed 77 -> 88 us with 296 of them), so keep them few — the rows are ~0.5 MB.
+    const int cap = pushed ? HALO_WARPS_OVERTAKING : (st == h->side ? HALO_WARPS_SIDE : HALO_WARPS_MAX);
+    nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
+    static bool carveout_set = false;
+    if (!carveout_set) {               // the same carve-out as the patch kernel: CTAs of both can share an SM
+        cudaFuncSetAttribute(k_halo_slot, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     // rows the fused patch kernel pushed: only wait and combine (and wait for the local rows, the launch may overtake
     // the gradient kernel); any other route to the gradient (gather kernel on small meshes, selections, other
     // functionals, a patch set freed by mcu_mesh_set_connectivity) leaves rows un-pushed: push them here
@@ -297,7 +313,19 @@ extern "C" int mcu_halo_status(mcu_halo *h) {
     unsigned s = 0;
     if (mcu_halo_join(h) != MCU_OK || cudaStreamSynchronize(mcu_stream()) != cudaSuccess) return MCU_ERR_CUDA;
     if (cudaMemcpy(&s, h->d_status, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return MCU_ERR_CUDA;
-    if (s) h->failed = true;             // later exchanges fail loudly instead of summing incomplete rows
+    if (s) {
+        h->failed = true;                // later exchanges fail loudly instead of summing incomplete rows
+        // what every rank was waiting for: per slot the completed-exchange count, the own-rows word and the peers' flags
+        int ctrl[72];
+        if (cudaMemcpy(ctrl, h->d_block, sizeof(ctrl), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            for (int slot = 0; slot < MCU_HALO_MAXSLOT; slot++) {
+                fprintf(stderr, "[mcu_halo] rank %d slot %d: exchanges completed %d, own rows at %d, peer flags", h->rank, slot,
+                        ctrl[MCU_HALO_EPOCH(slot)], ctrl[MCU_HALO_OWNDONE(slot)]);
+                for (int q = 0; q < h->world; q++) fprintf(stderr, " %d", ctrl[MCU_HALO_FLAG(slot, q)]);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     return (int) s;
 }
 

@@ -1057,6 +1057,100 @@ static value mc_translate_fn(vm *v, int nargs, value *args) {
 
 /* ------------------------------------------------------------------ extension entry points */
 
+
+/* ------------------------------------------------------------------ connectivity construction
+ * Mesh.addgrade(g) (mesh_addgrade, mesh.c:419-489: an n-tuple hash, ~4 us per candidate) and Selection(mesh, boundary=true)
+ * (selection_selectboundary, selection.c:211-232, which first builds the raise matrix with mesh_addlowermatrix,
+ * mesh.c:621-660) on the device for meshes large enough to matter (MORPHO_CUDA_CONNECT_MIN elements of the source grade,
+ * default 20000): mcu_connect.cu produces the same element ids in the same order, bit for bit.  The new incidence is
+ * handed to the reference as a compressed-column Sparse (sparseccs_resize, sparse.c:339-359) — the format
+ * mesh_freezeconnectivity converts every connectivity element into anyway. */
+static long mc_connect_min = 20000;
+bool selection_selectelement(objectselection *sel, grade g, elementid id);      /* selection.c:92, 129; mesh.c:96, 273 */
+bool selection_addgradelower(objectselection *sel, grade g);
+bool mesh_setconnectivityelement(objectmesh *mesh, unsigned int row, unsigned int col, objectsparse *el);
+void mesh_link(objectmesh *mesh, object *obj);
+static value mc_boundaryoption;       /* the interned symbol "boundary" (selection.c:568) */
+
+static builtinfunction orig_Mesh_addgrade = NULL;
+static value mc_Mesh_addgrade(vm *v, int nargs, value *args) {
+    objectmesh *mesh = MORPHO_GETMESH(MORPHO_SELF(args));
+    while (mc_ready && nargs == 1 && MORPHO_ISINTEGER(MORPHO_GETARG(args, 0))) {
+        int g = MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 0));
+        if (g < 1 || g > 2 || mesh_getconnectivityelement(mesh, 0, (unsigned) g)) break;
+        int maxg = (int) mesh_maxgrade(mesh), h;
+        objectsparse *el = NULL;
+        for (h = g + 1; h <= maxg && h <= 3; h++) if ((el = mesh_getconnectivityelement(mesh, 0, (unsigned) h))) break;
+        if (!el || !sparse_checkformat(el, SPARSE_CCS, true, false) || el->ccs.ncols < mc_connect_min) break;
+        mc_mirror *mr = mirror_get(mesh, (grade) h);
+        if (!mr || !mr->conn[h].ok) break;
+        for (int k = g; k < h; k++) { mcu_mesh_drop_connectivity(mr->m, k); mr->conn[k].ok = false; }   /* grades the Mesh no longer has */
+        int nel = 0;
+        if (mcu_mesh_addgrade(mr->m, g, &nel) != MCU_OK) { mc_log("addgrade not accelerated:", mcu_last_error()); break; }
+        objectsparse *new = object_newsparse(NULL, NULL);
+        if (!new) break;
+        if (!sparseccs_resize(&new->ccs, mr->nv, nel, (unsigned) ((size_t) nel * (g + 1)), false) ||
+            (nel > 0 && mcu_mesh_get_connectivity(mr->m, g, new->ccs.rix) != MCU_OK)) { object_free((object *) new); mcu_mesh_drop_connectivity(mr->m, g); break; }
+        for (int e = 0; e <= nel; e++) new->ccs.cptr[e] = e * (g + 1);
+        mesh_setconnectivityelement(mesh, 0, (unsigned) g, new);               /* mesh.c:483-485 */
+        mesh_link(mesh, (object *) new);
+        mesh_freezeconnectivity(mesh);
+        mr->conn[g].s = new; mr->conn[g].rix = new->ccs.rix; mr->conn[g].nel = nel; mr->conn[g].ok = true;   /* already on the device */
+        mc_stat_devops++;
+        return MORPHO_NIL;
+    }
+    return orig_Mesh_addgrade(v, nargs, args);
+}
+
+static builtinfunction orig_Selection_constructor = NULL;
+static value mc_Selection_constructor(vm *v, int nargs, value *args) {
+    value boundary = MORPHO_FALSE;
+    int nfixed = nargs;
+    while (mc_ready) {
+        builtin_options(v, nargs, args, &nfixed, 1, mc_boundaryoption, &boundary);
+        if (nfixed != 1 || !MORPHO_ISTRUE(boundary) || !MORPHO_ISMESH(MORPHO_GETARG(args, 0))) break;
+        objectmesh *mesh = MORPHO_GETMESH(MORPHO_GETARG(args, 0));
+        int maxg = (int) mesh_maxgrade(mesh);
+        if (maxg < 2 || maxg > 3) break;                       /* line meshes stay on the reference */
+        objectsparse *top = mesh_getconnectivityelement(mesh, 0, (unsigned) maxg), *fac = mesh_getconnectivityelement(mesh, 0, (unsigned) (maxg - 1));
+        if (!top || !fac || !sparse_checkformat(top, SPARSE_CCS, true, false) || top->ccs.ncols < mc_connect_min) break;
+        if (mesh_has_symmetries(mesh, (grade) maxg)) break;
+        mc_mirror *mr = mirror_get(mesh, (grade) maxg);
+        if (!mr || !mr->conn[maxg].ok) break;
+        mr = mirror_get(mesh, (grade) (maxg - 1));
+        if (!mr || !mr->conn[maxg - 1].ok) break;
+        int bg = 0, n = 0;
+        if (mcu_mesh_boundary(mr->m, &bg, &n, NULL, 0) != MCU_OK || bg != maxg - 1) { mc_log("boundary not accelerated:", mcu_last_error()); break; }
+        int *ids = malloc(sizeof(int) * (size_t) (n > 0 ? n : 1));
+        if (!ids) break;
+        if (mcu_mesh_boundary(mr->m, &bg, &n, ids, n) != MCU_OK) { free(ids); break; }
+        objectselection *new = object_newselection(mesh);
+        if (!new) { free(ids); break; }
+        for (int i = 0; i < n; i++) selection_selectelement(new, (grade) bg, ids[i]);     /* ascending ids: the reference's insertion order */
+        free(ids);
+        selection_addgradelower(new, 0);
+        mc_stat_devops++;
+        value out = MORPHO_OBJECT(new);
+        morpho_bindobjects(v, 1, &out);
+        return out;
+    }
+    return orig_Selection_constructor(v, nargs, args);
+}
+
+static int patch_function(const char *name, builtinfunction ours, builtinfunction *orig) {
+    objectstring key = MORPHO_STATICSTRING((char *) name);
+    value fv;
+    if (!dictionary_get(&builtin_functiontable, MORPHO_OBJECT(&key), &fv) || !MORPHO_ISBUILTINFUNCTION(fv)) {
+        fprintf(stderr, "[morphocuda] function %s not found as a single builtin; left alone\n", name);
+        return 0;
+    }
+    objectbuiltinfunction *f = MORPHO_GETBUILTINFUNCTION(fv);
+    if (f->function == ours) return 1;
+    *orig = f->function;
+    f->function = ours;
+    return 1;
+}
+
 #define PATCH(cls, meth) npatched += patch_method(#cls, #meth, mc_##cls##_##meth, &orig_##cls##_##meth)
 
 /* Everything that is done once per process, whichever of `import morphocuda` / `import functionals` comes first. */
@@ -1139,6 +1233,14 @@ static void mc_core_initialize(void) {
     PATCH(LineIntegral, total); PATCH(LineIntegral, integrand); PATCH(LineIntegral, gradient); PATCH(LineIntegral, fieldgradient);
     PATCH(AreaIntegral, total); PATCH(AreaIntegral, integrand); PATCH(AreaIntegral, gradient); PATCH(AreaIntegral, fieldgradient);
     PATCH(VolumeIntegral, total); PATCH(VolumeIntegral, integrand); PATCH(VolumeIntegral, gradient); PATCH(VolumeIntegral, fieldgradient);
+    /* (5) connectivity construction on the device */
+    const char *cmin = getenv("MORPHO_CUDA_CONNECT_MIN");
+    if (cmin) mc_connect_min = atol(cmin);
+    if (mc_connect_min >= 0) {
+        mc_boundaryoption = builtin_internsymbolascstring(SELECTION_BOUNDARYOPTION);
+        npatched += patch_method("Mesh", MESH_ADDGRADE_METHOD, mc_Mesh_addgrade, &orig_Mesh_addgrade);
+        npatched += patch_function(SELECTION_CLASSNAME, mc_Selection_constructor, &orig_Selection_constructor);
+    }
 
     object probe;
     memset(&probe, 0, sizeof(probe));

@@ -122,6 +122,104 @@ def config5(mb, torch, hbm_peak, n=204, reps=3):
     return res
 
 
+def config5_partitioned(mb, torch, dist, hbm_peak, n=204, reps=3, log=print):
+    """BASELINE config 5 as north_star states it: the ~50M-tetrahedron cube ELEMENT-PARTITIONED over the ranks
+    (contiguous element ranges, functional_binbounds functional.c:863-879): every rank evaluates Volume.gradient,
+    GradSq(5).fieldgradient and Nematic.fieldgradient on its range and the rows of vertices shared between ranks are
+    completed over NVLink peer memory (mcu_halo.cu; 3, 5 and 3 doubles per vertex) and summed in rank order.
+    Strong scaling (total work fixed).  Before timing, every rank's completed rows are compared with the same
+    evaluation of the UNDIVIDED mesh on rank 0 (the single-GPU path the parity tests pin to the oracle)."""
+    from morpho_b200 import _lib, meshgen as mg
+    from morpho_b200.partition import PeerExchange, partition_arrays
+    L = mb.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t0 = time.time()
+    v, tets = mg.tet_cube(n)
+    rng = np.random.Generator(np.random.PCG64(12345))
+    inner = np.all((v > 1e-9) & (v < 1 - 1e-9), axis=1)
+    v = v + (0.2 / n) * rng.uniform(-1, 1, size=v.shape) * inner[:, None]
+    q = np.stack([v[:, 0], 2 * v[:, 1], -v[:, 2], v[:, 0] + v[:, 1], 0 * v[:, 0] + 3.0], axis=1) + 0.01 * rng.standard_normal((v.shape[0], 5))
+    nn = np.stack([np.cos(v[:, 0] + 0.3 * v[:, 1]), np.sin(v[:, 0] + 0.3 * v[:, 1]), 0.2 * np.sin(4 * v[:, 2])], axis=1)
+    nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    rm = partition_arrays(v, tets, world)[rank]
+    nel = tets.shape[0]
+    t_part = time.time() - t0
+
+    def functionals(mesh, fq, fn):
+        return ((mb.Volume(), "Volume.gradient", _lib.MCU_GRADIENT, 3, 24.0),
+                (mb.GradSq(fq), "GradSq(5).fieldgradient", _lib.MCU_FIELDGRADIENT, 5, 20.0 + 80.0 / 6),
+                (mb.Nematic(fn, ksplay=1.0, ktwist=0.8, kbend=1.2), "Nematic.fieldgradient", _lib.MCU_FIELDGRADIENT, 3, 20.0 + 48.0 / 6))
+
+    # the undivided mesh on rank 0, results broadcast to everybody
+    full = {}
+    if rank == 0:
+        mfull = mb.Mesh(v, volumes=tets)
+        fqf, fnf = mb.Field(mfull, q), mb.Field(mfull, nn)
+        for f, name, mode, dim, _ in functionals(mfull, fqf, fnf):
+            out = torch.empty(v.shape[0] * dim, dtype=torch.float64, device="cuda")
+            d = f._desc(0)
+            _lib.check(L.mcu_eval_device(mfull._h, C.byref(d), None, mode, out.data_ptr()))
+            L.mcu_sync()
+            full[name] = out
+        del fqf, fnf, mfull
+    else:
+        for name, dim in (("Volume.gradient", 3), ("GradSq(5).fieldgradient", 5), ("Nematic.fieldgradient", 3)):
+            full[name] = torch.empty(v.shape[0] * dim, dtype=torch.float64, device="cuda")
+    for name in ("Volume.gradient", "GradSq(5).fieldgradient", "Nematic.fieldgradient"):
+        dist.broadcast(full[name], 0)
+
+    mesh = mb.Mesh(rm.vert, volumes=rm.conn)
+    fq, fn = mb.Field(mesh, q[rm.gids]), mb.Field(mesh, nn[rm.gids])
+    gid_t = torch.as_tensor(rm.gids, dtype=torch.int64, device="cuda")
+    res = {"workload": f"unit cube, {nel} tetrahedra, {v.shape[0]} vertices ({n}^3 cells x 6) partitioned by contiguous element ranges over {world} GPUs "
+                       f"({rm.conn.shape[0]} tetrahedra, {rm.vert.shape[0]} vertices, {rm.n_shared} shared on rank 0); strong scaling",
+           "kernels": {}, "parity_vs_undivided_mesh": {}}
+    stream = torch.cuda.current_stream()
+    for f, name, mode, dim, bpe in functionals(mesh, fq, fn):
+        out = torch.empty(rm.vert.shape[0] * dim, dtype=torch.float64, device="cuda")
+        ex = PeerExchange(rm, torch, dist, ngrad=1, dim=dim)
+        d = f._desc(0)
+
+        def step(evs=None):
+            if evs: evs[0].record(stream)
+            _lib.check(L.mcu_eval_device(mesh._h, C.byref(d), None, mode, out.data_ptr()))
+            if evs: evs[1].record(stream)
+            ex(out)
+            if evs: evs[2].record(stream)
+
+        step()
+        L.mcu_sync()
+        if ex.status() != 0:
+            raise RuntimeError("halo exchange: a peer did not arrive in time")
+        want = full[name].view(-1, dim).index_select(0, gid_t)
+        got = out.view(-1, dim)
+        err = torch.linalg.norm(got - want, dim=1).max() / torch.linalg.norm(full[name].view(-1, dim), dim=1).max()
+        err_t = err.reshape(1).clone()
+        dist.all_reduce(err_t, op=dist.ReduceOp.MAX)
+        res["parity_vs_undivided_mesh"][name] = float(err_t.item())
+        dist.barrier(); torch.cuda.synchronize()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+        for k in range(reps):
+            step(evs[k])
+        dist.barrier(); torch.cuda.synchronize()
+        ts = torch.tensor([float(np.mean([e[0].elapsed_time(e[2]) for e in evs])), float(np.mean([e[0].elapsed_time(e[1]) for e in evs])),
+                           float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms, ms_k, ms_x = [float(x) for x in ts.cpu()]
+        gbs = bpe * nel / (ms * 1e-3) / 1e9
+        res["kernels"][name] = {"ms": ms, "kernel_ms": ms_k, "shared_row_exchange_ms": ms_x, "gelem_per_s": nel / (ms * 1e-3) / 1e9,
+                                "bytes_per_element": bpe, "achieved_gbs_all_gpus": gbs, "frac_of_n_gpu_roofline": gbs / (hbm_peak * world)}
+        ex.close()
+    res["partition_s"] = t_part
+    res["value"] = res["kernels"]["Volume.gradient"]["gelem_per_s"]
+    res["unit"] = f"G element-evals/s (Volume.gradient, {world} GPUs, whole job)"
+    res["frac"] = res["kernels"]["Volume.gradient"]["frac_of_n_gpu_roofline"]
+    worst = max(res["parity_vs_undivided_mesh"].values())
+    if worst > 1e-12:
+        raise RuntimeError(f"partitioned config 5 disagrees with the undivided mesh: {res['parity_vs_undivided_mesh']}")
+    return res
+
+
 def run_all(mb, torch, hbm_peak, which=("3", "4", "5"), log=print):
     out = {}
     for key, fn in (("3", config3), ("4", config4), ("5", config5)):

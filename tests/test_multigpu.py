@@ -112,7 +112,7 @@ def test_partitioned_gradient_over_peer_memory():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 60, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 160, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
