@@ -68,7 +68,6 @@ extern "C" int mcu_halo_join(mcu_halo *h);
 static int halo_join_slot(mcu_halo *h, int slot);
 
 #define HALO_WARPS_MAX 296           // single-warp CTAs: two per SM
-#define HALO_WARPS_SIDE 32           // ... on the second stream, beside the next gradient kernel
 #define HALO_WARPS_OVERTAKING 48     // ... when the launch can get in front of the kernel whose rows it waits for (see halo_slot_launch)
 
 // One launch per (exchange, slot).  Single-warp CTAs.
@@ -228,10 +227,11 @@ static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cu
     // cannot take a CTA of the patch kernel when the two kernels ask for different shared-memory carve-outs (the
     // patch kernel needs the largest one) — with a spinning CTA on every SM the gradient kernel never starts and both
     // sit there until the time-out (seen at N = 2 with >= 1500 shared vertices: 199-296 CTAs on 148 SMs).
-    // On the second stream the launch shares the SMs with the next gradient kernel, whose persistent CTAs want all of an
-    // SM's shared memory: every SM that hosts one of these warps runs that kernel with one CTA instead of two until the
-    // warp is gone (VolumeEnclosed 77 -> 88 us with 296 of them), so keep them few — the rows are ~0.5 MB.
-    const int cap = pushed ? HALO_WARPS_OVERTAKING : (st == h->side ? HALO_WARPS_SIDE : HALO_WARPS_MAX);
+    // On the second stream the launch shares the SMs with the next gradient kernel (VolumeEnclosed 77 -> 88 us beside 296
+    // of these warps at N = 2).  Fewer warps are NOT the answer: the loops below are chains of dependent loads, and with
+    // 32 warps the exchange of 11 414 shared rows at N = 8 took ~100 us per gradient instead of ~30
+    // (profiles/r2_bench_n8_sidecap32.json against profiles/r2_bench_n2.json).
+    const int cap = pushed ? HALO_WARPS_OVERTAKING : HALO_WARPS_MAX;
     nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
     static bool carveout_set = false;
     if (!carveout_set) {               // the same carve-out as the patch kernel: CTAs of both can share an SM

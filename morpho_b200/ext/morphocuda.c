@@ -1077,13 +1077,13 @@ static value mc_Mesh_addgrade(vm *v, int nargs, value *args) {
     objectmesh *mesh = MORPHO_GETMESH(MORPHO_SELF(args));
     while (mc_ready && nargs == 1 && MORPHO_ISINTEGER(MORPHO_GETARG(args, 0))) {
         int g = MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 0));
-        if (g < 1 || g > 2 || mesh_getconnectivityelement(mesh, 0, (unsigned) g)) break;
+        if (g < 1 || g > 2 || mesh_getconnectivityelement(mesh, 0, (unsigned) g)) break;        /* nothing to build, or not ours */
         int maxg = (int) mesh_maxgrade(mesh), h;
         objectsparse *el = NULL;
         for (h = g + 1; h <= maxg && h <= 3; h++) if ((el = mesh_getconnectivityelement(mesh, 0, (unsigned) h))) break;
-        if (!el || !sparse_checkformat(el, SPARSE_CCS, true, false) || el->ccs.ncols < mc_connect_min) break;
+        if (!el || !sparse_checkformat(el, SPARSE_CCS, true, false) || el->ccs.ncols < mc_connect_min) { mc_log("addgrade on the reference:", "source grade absent or below MORPHO_CUDA_CONNECT_MIN"); break; }
         mc_mirror *mr = mirror_get(mesh, (grade) h);
-        if (!mr || !mr->conn[h].ok) break;
+        if (!mr || !mr->conn[h].ok) { mc_log("addgrade on the reference:", "no mirror of the source grade"); break; }
         for (int k = g; k < h; k++) { mcu_mesh_drop_connectivity(mr->m, k); mr->conn[k].ok = false; }   /* grades the Mesh no longer has */
         int nel = 0;
         if (mcu_mesh_addgrade(mr->m, g, &nel) != MCU_OK) { mc_log("addgrade not accelerated:", mcu_last_error()); break; }
@@ -1108,17 +1108,17 @@ static value mc_Selection_constructor(vm *v, int nargs, value *args) {
     int nfixed = nargs;
     while (mc_ready) {
         builtin_options(v, nargs, args, &nfixed, 1, mc_boundaryoption, &boundary);
-        if (nfixed != 1 || !MORPHO_ISTRUE(boundary) || !MORPHO_ISMESH(MORPHO_GETARG(args, 0))) break;
+        if (nfixed != 1 || !MORPHO_ISTRUE(boundary) || !MORPHO_ISMESH(MORPHO_GETARG(args, 0))) break;       /* not a boundary selection */
         objectmesh *mesh = MORPHO_GETMESH(MORPHO_GETARG(args, 0));
         int maxg = (int) mesh_maxgrade(mesh);
         if (maxg < 2 || maxg > 3) break;                       /* line meshes stay on the reference */
         objectsparse *top = mesh_getconnectivityelement(mesh, 0, (unsigned) maxg), *fac = mesh_getconnectivityelement(mesh, 0, (unsigned) (maxg - 1));
-        if (!top || !fac || !sparse_checkformat(top, SPARSE_CCS, true, false) || top->ccs.ncols < mc_connect_min) break;
+        if (!top || !fac || !sparse_checkformat(top, SPARSE_CCS, true, false) || top->ccs.ncols < mc_connect_min) { mc_log("boundary on the reference:", "facet grade absent or mesh below MORPHO_CUDA_CONNECT_MIN"); break; }
         if (mesh_has_symmetries(mesh, (grade) maxg)) break;
         mc_mirror *mr = mirror_get(mesh, (grade) maxg);
-        if (!mr || !mr->conn[maxg].ok) break;
+        if (!mr || !mr->conn[maxg].ok) { mc_log("boundary on the reference:", "no mirror of the top grade"); break; }
         mr = mirror_get(mesh, (grade) (maxg - 1));
-        if (!mr || !mr->conn[maxg - 1].ok) break;
+        if (!mr || !mr->conn[maxg - 1].ok) { mc_log("boundary on the reference:", "no mirror of the facet grade"); break; }
         int bg = 0, n = 0;
         if (mcu_mesh_boundary(mr->m, &bg, &n, NULL, 0) != MCU_OK || bg != maxg - 1) { mc_log("boundary not accelerated:", mcu_last_error()); break; }
         int *ids = malloc(sizeof(int) * (size_t) (n > 0 ? n : 1));

@@ -153,6 +153,23 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_connectivity_is_built_on_the_device(tmp_path):
+    """SURVEY 8f N2 behind the script API: Mesh.addgrade (mesh.c:419-489) and Selection(mesh, boundary=true)
+    (selection.c:211-232) through mcu_connect.cu — element ids, their order and the selected sets are the reference's,
+    character for character; 6 constructions ran on the device."""
+    src = script("connectivity.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho",
+                   {"MORPHO_CUDA_VERBOSE": "1", "MORPHO_CUDA_CONNECT_MIN": "1000"})
+    assert ref == new[:-1], (ref, new, err)
+    stats = [int(float(v)) for v in NUM.findall(new[-1])]
+    assert stats[6] >= 6, (stats, err)              # device operations: 4 addgrade (AreaMesh already made the edges once) + 2 boundary selections
+    # below the threshold everything stays on the reference
+    new2, _ = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext2.morpho", {"MORPHO_CUDA_CONNECT_MIN": "100000000"})
+    assert ref == new2[:-1]
+
+
+@pytest.mark.gpu
 def test_volume_integral_closures_run_on_the_gpu(tmp_path):
     """VolumeIntegral (functional.c:5471-5576) with the default integrator integrate_volint (integrate.c:677-752) on a
     162-tetrahedron lattice: totals / integrands at 1e-12, finite-difference gradients at the FD tolerance; no fallbacks."""
