@@ -701,7 +701,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the gradients before timing")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3/4/5 (N=1 only)")
-    ap.add_argument("--watchdog", type=int, default=1500, help="N > 1: seconds after which a run that has not finished kills itself")
+    ap.add_argument("--watchdog", type=int, default=900, help="N > 1: seconds after which a run that has not finished kills itself")
     ap.add_argument("--tets", type=int, default=204, help="N > 1: cells per edge of the config-5 tetrahedral cube (204 = BASELINE config 5)")
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
