@@ -706,9 +706,10 @@ def main():
     ap.add_argument("--patch-owned", type=int, default=0, help="override the number of owned vertices per patch")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mcu_set_option), repeatable")
     ap.add_argument("--quick", action="store_true", help="kernel timing only: skip the end-to-end leg")
-    ap.add_argument("--exchange", default="overlap", choices=["overlap", "serial", "nccl"],
-                    help="multi-GPU completion of shared rows: peer-memory exchange on a second stream underneath the gradient kernels "
-                         "(default), the same exchange serialised behind them, or one ncclAllReduce of the packed rows (comparison)")
+    ap.add_argument("--exchange", default="serial", choices=["overlap", "serial", "nccl"],
+                    help="multi-GPU completion of shared rows: ONE peer-memory exchange kernel for both gradients behind the gradient kernels "
+                         "(default: 192.6 G at N = 2), one exchange per gradient on a second stream underneath the next kernel (188.9 G: the "
+                         "co-running exchange slows VolumeEnclosed by 11 us), or one ncclAllReduce of the packed rows (159.0 G; comparison)")
     ap.add_argument("--scaling", default="both", choices=["both", "weak", "strong"],
                     help="N > 1: the headline line is weak scaling (N x 10M triangles); 'both' adds a strong-scaling leg (the 10M-triangle sphere "
                          "cut N ways) as `strong_scaling`; 'strong' makes the 10M-triangle sphere the only workload")

@@ -68,30 +68,37 @@ extern "C" int mcu_halo_join(mcu_halo *h);
 static int halo_join_slot(mcu_halo *h, int slot);
 
 #define HALO_WARPS_MAX 296           // single-warp CTAs: two per SM
+#define HALO_WARPS_ALONE 2048        // ... alone on the library stream
 #define HALO_WARPS_OVERTAKING 48     // ... when the launch can get in front of the kernel whose rows it waits for (see halo_slot_launch)
 
 // One launch per (exchange, slot).  Single-warp CTAs.
 __global__ void __maxnreg__(32)
-k_halo_slot(double *__restrict__ grad, int dim, int slot, const int *__restrict__ shared_local,
+k_halo_slot(double *__restrict__ grad, double *__restrict__ grad2, int nslots, int dim, int slot, const int *__restrict__ shared_local,
             const int *__restrict__ peer_ptr, const int *__restrict__ peer_pos, void *const *__restrict__ peer_block,
             const int *__restrict__ contrib_ptr, const int *__restrict__ contrib_rank, const int *__restrict__ contrib_k,
             unsigned char *block, size_t recv_off, int rank, int world, int max_m, int ncomp, int n_pairs,
             int n_shared, unsigned *counter, unsigned *status, int wait_own, long long timeout_cycles) {
     volatile int *ctrl = (volatile int *) block;
-    // the epoch cannot move while any CTA of this launch is alive: it is bumped by the LAST CTA to finish
+    // One launch completes `nslots` (1 or 2) consecutive column blocks: grad -> block `slot`, grad2 -> block `slot + 1`.
+    // Flags and the wait use the FIRST block's epoch; every block keeps its own epoch counter (and with it its own buffer
+    // parity), bumped together at the end, so merged and single exchanges of a block can follow each other in any order.
+    // The epochs cannot move while any CTA of this launch is alive: they are bumped by the LAST CTA to finish.
     const int epoch = ctrl[MCU_HALO_EPOCH(slot)] + 1;
-    const int parity = epoch & 1;
-    const int col0 = slot * dim;
+    const int parity0 = epoch & 1;
+    const int parity1 = nslots > 1 ? ((ctrl[MCU_HALO_EPOCH(slot + 1)] + 1) & 1) : 0;
     const int lane = threadIdx.x;
     if (n_pairs > 0) {
         // push phase (the gradient did not come from the fused patch kernel): this launch is stream-ordered behind it
-        for (int t = blockIdx.x * 32 + lane; t < n_pairs; t += gridDim.x * 32) {
+        for (int t = blockIdx.x * 32 + lane; t < n_pairs * nslots; t += gridDim.x * 32) {
+            const int sl = t >= n_pairs ? 1 : 0, tp = t - sl * n_pairs;
             int q = 0;
-            while (q + 1 < world && peer_ptr[q + 1] <= t) q++;
-            const int k = t - peer_ptr[q];
-            const int v = shared_local[peer_pos[t]];
-            double *dst = (double *) ((unsigned char *) peer_block[q] + recv_off) + (((size_t) parity * world + rank) * max_m + k) * ncomp + col0;
-            for (int c = 0; c < dim; c++) dst[c] = grad[(size_t) v * dim + c];   // remote stores
+            while (q + 1 < world && peer_ptr[q + 1] <= tp) q++;
+            const int k = tp - peer_ptr[q];
+            const int v = shared_local[peer_pos[tp]];
+            const double *src = (sl ? grad2 : grad) + (size_t) v * dim;
+            double *dst = (double *) ((unsigned char *) peer_block[q] + recv_off) +
+                          (((size_t) (sl ? parity1 : parity0) * world + rank) * max_m + k) * ncomp + (slot + sl) * dim;
+            for (int c = 0; c < dim; c++) dst[c] = src[c];                       // remote stores
         }
         __threadfence_system();
         __syncwarp();
@@ -120,17 +127,21 @@ k_halo_slot(double *__restrict__ grad, int dim, int slot, const int *__restrict_
     good = __shfl_sync(0xffffffffu, good, 0);
     if (good) {
         const double *recv = (const double *) (block + recv_off);
-        for (int t = blockIdx.x * 32 + lane; t < n_shared * dim; t += gridDim.x * 32) {
-            const int i = t / dim, c = t - i * dim;
+        const int per = n_shared * dim;
+        for (int t = blockIdx.x * 32 + lane; t < per * nslots; t += gridDim.x * 32) {
+            const int sl = t >= per ? 1 : 0, tt = t - sl * per;
+            const int i = tt / dim, c = tt - i * dim;
             const int v = shared_local[i];
-            const double own = __ldcv(grad + (size_t) v * dim + c);
+            double *g = (sl ? grad2 : grad) + (size_t) v * dim + c;
+            const int parity = sl ? parity1 : parity0, col0 = (slot + sl) * dim;
+            const double own = __ldcv(g);
             double sum = 0.0;
             for (int j = contrib_ptr[i]; j < contrib_ptr[i + 1]; j++) {
                 const int q = contrib_rank[j], k = contrib_k[j];
                 const double x = (k < 0) ? own : __ldcv(recv + (((size_t) parity * world + q) * max_m + k) * ncomp + col0 + c);
                 sum = __dadd_rn(sum, x);                  // ascending rank order, identical on every sharing rank
             }
-            grad[(size_t) v * dim + c] = sum;
+            *g = sum;
         }
     }
     __threadfence();
@@ -138,7 +149,8 @@ k_halo_slot(double *__restrict__ grad, int dim, int slot, const int *__restrict_
     if (lane == 0 && atomicAdd(counter + 4 + slot, 1u) == gridDim.x - 1) {
         counter[4 + slot] = 0;
         __threadfence();
-        ctrl[MCU_HALO_EPOCH(slot)] = epoch;               // this exchange of the slot is complete
+        if (nslots > 1) ctrl[MCU_HALO_EPOCH(slot + 1)] = ctrl[MCU_HALO_EPOCH(slot + 1)] + 1;
+        ctrl[MCU_HALO_EPOCH(slot)] = epoch;               // this exchange of the column block(s) is complete
     }
 }
 
@@ -213,14 +225,16 @@ extern "C" int mcu_halo_connect(mcu_halo *h, const unsigned char *handles) {
     return MCU_OK;
 }
 
-static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cudaStream_t st) {
+static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cudaStream_t st, double *dev_grad2 = nullptr) {
+    const int nslots = dev_grad2 ? 2 : 1;
     const bool pushed = h->fused && slot < 32 && (h->pushed_mask & (1u << slot));
     if (slot < 32) h->pushed_mask &= ~(1u << slot);
+    if (nslots > 1 && slot + 1 < 32) h->pushed_mask &= ~(1u << (slot + 1));
     {
         long ms = mcu_opt("halo_timeout_ms", 0);
         if (ms > 0) h->timeout_cycles = (long long) ms * 2000000LL;
     }
-    const int work = std::max(pushed ? 0 : h->n_pairs, h->n_shared * dim);
+    const int work = nslots * std::max(pushed ? 0 : h->n_pairs, h->n_shared * dim);
     int nb = (work + 31) / 32;
     // A launch that may OVERTAKE the gradient kernel it waits for (fused pushes, second stream) must leave most SMs
     // alone: its CTAs spin until the gradient kernel has written the own rows, and an SM that hosts a spinning CTA
@@ -231,7 +245,11 @@ static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cu
     // of these warps at N = 2).  Fewer warps are NOT the answer: the loops below are chains of dependent loads, and with
     // 32 warps the exchange of 11 414 shared rows at N = 8 took ~100 us per gradient instead of ~30
     // (profiles/r2_bench_n8_sidecap32.json against profiles/r2_bench_n2.json).
-    const int cap = pushed ? HALO_WARPS_OVERTAKING : HALO_WARPS_MAX;
+    // On the library stream nothing else runs beside the exchange: as many warps as there are rows (one item per lane
+    // and phase — with 296 warps the merged exchange of 2 x 10 000 rows took 47 us, all of it load latency).  Every CTA
+    // of a launch has to be resident at once (a CTA waits for the peers' flags, and those are raised only after ALL CTAs
+    // of the peer's launch have pushed): 2048 single-warp CTAs are 14 per SM, under the 32 an SM holds.
+    const int cap = pushed ? HALO_WARPS_OVERTAKING : (st == h->side ? HALO_WARPS_MAX : HALO_WARPS_ALONE);
     nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
     static bool carveout_set = false;
     if (!carveout_set) {               // the same carve-out as the patch kernel: CTAs of both can share an SM
@@ -241,7 +259,7 @@ static int halo_slot_launch(mcu_halo *h, int slot, double *dev_grad, int dim, cu
     // rows the fused patch kernel pushed: only wait and combine (and wait for the local rows, the launch may overtake
     // the gradient kernel); any other route to the gradient (gather kernel on small meshes, selections, other
     // functionals, a patch set freed by mcu_mesh_set_connectivity) leaves rows un-pushed: push them here
-    k_halo_slot<<<nb, 32, 0, st>>>(dev_grad, dim, slot, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
+    k_halo_slot<<<nb, 32, 0, st>>>(dev_grad, dev_grad2, nslots, dim, slot, h->d_shared_local, h->d_peer_ptr, h->d_peer_pos, h->d_peer_block,
                                    h->d_contrib_ptr, h->d_contrib_rank, h->d_contrib_k, h->d_block, h->recv_off, h->rank, h->world,
                                    h->max_m, h->ncomp, pushed ? 0 : h->n_pairs, h->n_shared, h->d_counter, h->d_status, pushed ? 1 : 0,
                                    h->timeout_cycles);
@@ -263,7 +281,15 @@ extern "C" int mcu_halo_exchange(mcu_halo *h, int ngrad, double *const *dev_grad
     if (rc) return rc;
     if (h->world == 1 || h->n_shared == 0) return MCU_OK;
     rc = mcu_halo_join(h);
-    for (int s = 0; s < ngrad && !rc; s++) rc = halo_slot_launch(h, s, dev_grads[s], dim, mcu_stream());
+    // Two gradients whose rows all have to be pushed here go in ONE launch: one flag round trip instead of two
+    // ("halo_merge" = 0 keeps one launch per gradient).  Rows the fused patch kernel already pushed keep the
+    // per-gradient launches (their flags were raised per column block).
+    const bool any_pushed = h->fused && (h->pushed_mask & ((1u << ngrad) - 1u));
+    const bool merge = mcu_opt("halo_merge", 1) != 0 && !any_pushed;
+    for (int s = 0; s < ngrad && !rc;) {
+        if (merge && s + 1 < ngrad) { rc = halo_slot_launch(h, s, dev_grads[s], dim, mcu_stream(), dev_grads[s + 1]); s += 2; }
+        else { rc = halo_slot_launch(h, s, dev_grads[s], dim, mcu_stream()); s += 1; }
+    }
     return rc;
 }
 

@@ -43,6 +43,7 @@ def _worker(rank, world, port, f, q):
         errs = []
         mb.set_option("gradient_path", _lib.MCU_PATH_PATCH)
         for rep in range(8):                           # several exchanges: alternating receive buffers, epochs
+            mb.set_option("halo_merge", 0 if rep == 1 else 1)   # rep 1: one exchange launch per gradient; else both gradients in one
             if rep == 3:
                 ex.attach(mesh)                        # fused mode: the gradient kernel pushes the shared rows itself
             for slot, (g, cls) in enumerate(zip(grads, (mb.Area, mb.VolumeEnclosed))):
