@@ -230,6 +230,21 @@ int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int 
 int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                           mcu_selection *sel, int wrt, double *host_out);
 
+/* The same with the reference's RULE-TABLE integrator, which a `method` dictionary selects (integrate(),
+ * integrate.c:2849-2866; integrator_configurewithdictionary 2706-2751): `rule` = the "rule" entry (empty: none), `degree` =
+ * the "degree" entry (< 0: none), `adapt` = the "adapt" entry (default true).  Rule selection follows
+ * integrator_configure (2652-2704): by name, else the lowest rule of at least that degree, else the default of the grade
+ * (gauss5, cubtri7, grundmann3d0); the extension chain of the rule (or a second rule of higher degree) gives the error
+ * estimate; the worst work item is bisected / quadrisected / cut into eight until the summed error is below 1e-6 of the
+ * value (integrator_integrate, 2759-2835).  method == NULL: the default integrator above.  MCU_ERR_UNSUPPORTED when the
+ * reference would raise IntgrtrRlNtFnd / IntgrtrRlUnavlb / IntgrtrSbdvsns or an element needs more work items than the
+ * device keeps per element (256 / 157 / 102 for lines / triangles / tetrahedra): the caller leaves the call to the reference. */
+typedef struct mcu_quad_method { int adapt; int degree; char rule[32]; } mcu_quad_method;
+int mcu_integral_method(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                        mcu_selection *sel, int mode, const mcu_quad_method *method, double *host_out);
+int mcu_integral_gradient_method(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                                 mcu_selection *sel, int wrt, const mcu_quad_method *method, double *host_out);
+
 /* ---- ScalarPotential (functional.c:2255-2372): a function of the position evaluated at every (selected) vertex, given
  *      as a postfix program over MCU_X_POS (no field / element ops).  nprog programs are concatenated in progs, program k
  *      has nops[k] ops.  MCU_TOTAL (1 double) and MCU_INTEGRAND (nv doubles): nprog = 1.  MCU_GRADIENT (nv * dim
@@ -322,6 +337,10 @@ int mcu_debug_block_plan(int nv, int dim, int n, int nvper, const int *rix, cons
 int mcu_debug_patch_triangles(int nv, int nel, const int *rix, const double *vert, int max_owned,
                               long *n_words_out, int *tri_hdr_out, unsigned *tri_out);
 int mcu_debug_patch_profile(long long *dev_buf);
+/* the quadrature rules in the order of quadrules[] (integrate.c:1958-1975): info = grade, order, nnodes, index of the
+ * extension rule or -1, number of weights; and integrator_configure's choice (rule, error rule or -1) */
+int mcu_debug_quadrule(int index, char name[32], int info[5], double *nodes, double *weights, int cap);
+int mcu_debug_quadconfigure(int grade, int adapt, int degree, const char *name, int out[2]);
 
 #ifdef __cplusplus
 }

@@ -134,6 +134,10 @@ def lib():
         "mcu_halo_bind": (C.c_int, [vp, C.c_int]),
         "mcu_halo_destroy": (C.c_int, [vp]),
         "mcu_debug_patch_profile": (C.c_int, [vp]),
+        "mcu_debug_quadrule": (C.c_int, [C.c_int, vp, ip, vp, vp, C.c_int]),
+        "mcu_debug_quadconfigure": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, ip]),
+        "mcu_integral_method": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+        "mcu_integral_gradient_method": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
         "mcu_debug_patch_plan": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_long), vp, vp, vp]),
         "mcu_debug_block_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_long), vp, vp, vp]),
     }

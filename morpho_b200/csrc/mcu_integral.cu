@@ -31,6 +31,7 @@
 
 #include "mcu_host.h"
 #include "mcu_integrands.cuh"      // perpendicular / p1grad_tri: the P1 gradient of GradSq, reused by grad()
+#include "mcu_quadrules.h"
 
 extern long g_mcu_launches;
 
@@ -55,6 +56,28 @@ struct MiRules {
 __constant__ MiRules c_rules;
 __constant__ mcu_expr_op c_prog[MI_MAXOPS];
 
+// ---- the rule-table integrator (integrate.c:2168-2865), selected by a `method` dictionary ---------------------------
+// A configured integrator is a CHAIN of rules rule -> ext -> ext ... over one node array (an extension re-uses the
+// function values of the rule it extends) and, when the rule has no extension, a second chain for the error rule.
+#define MQ_MAXLEV 6
+#define MQ_MAXNODES 126
+#define MQ_MAXW 256
+#define MQ_ZTOL 1e-15           // INTEGRATE_ZEROCHECK
+#define MQ_MAXIT 1000           // INTEGRATE_MAXITERATIONS
+struct MqChain {
+    int nlev, nn[MQ_MAXLEV], woff[MQ_MAXLEV];
+    double nodes[MQ_MAXNODES * 4];
+    double w[MQ_MAXW];
+};
+struct MqMethod {
+    int adapt, has_err;
+    MqChain main, err;
+};
+__constant__ MqMethod c_method;
+// subdivision rules (integrate.c:1988-2157): new points = midpoints, new elements by vertex index (original vertices first)
+__constant__ unsigned char c_sub_line[2][2] = {{2, 1}, {0, 2}};
+__constant__ unsigned char c_sub_tri[4][3] = {{0, 3, 5}, {3, 1, 4}, {3, 4, 5}, {5, 4, 2}};
+
 struct MiView {
     int dim, g, nops, nq, nel;
     const double *vert;
@@ -68,6 +91,8 @@ struct MiView {
     int nq_in;                                 // components read from fields; the rest are derived
     int tn_slot;                               // first of 3 slots holding the tangent (g = 1) / normal (g = 2), or -1
     int ngrad, gsrc[MI_MAXG], gslot[MI_MAXG];  // gradient of component gsrc[i] in slots gslot[i] .. +2
+    int method;                                // 0: integrate_integrate (the default integrator); 1: c_method
+    unsigned *fail;                            // device word: set when an element needs more work items than a thread holds
 };
 
 // the postfix machine: ops c_prog[off .. off + len)
@@ -249,6 +274,161 @@ __device__ double mi_tet(const MiView &v, const double (*xv)[3], const double (*
     return sum;
 }
 
+// One work item: weight, value, lower-order value, error estimate and the element's vertices in the barycentric
+// coordinates of the ROOT element (the reference keeps them on a vertex stack and refers to them by id).
+template <int NB> struct MqItem { double weight, val, lval, err; double v[NB * NB]; };
+
+// integrator_quadrature (integrate.c:2445-2504) with `chain` as rule -> ext -> ...
+template <int NB>
+__device__ void mq_chain(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ], const MqChain &ch, MqItem<NB> &it, double *f) {
+    auto evalfn = [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            double lam[NB];
+            for (int j = 0; j < NB; j++) lam[j] = 0.0;
+            for (int k = 0; k < NB; k++) for (int j = 0; j < NB; j++) lam[j] += it.v[k * NB + j] * ch.nodes[i * NB + k];   // integrator_transformtorefelement
+            f[i] = mi_at<NB>(v, xv, qv, lam);
+        }
+    };
+    auto wsum = [&](int lev) { double r = 0.0; for (int i = 0; i < ch.nn[lev]; i++) r += f[i] * ch.w[ch.woff[lev] + i]; return r; };
+    evalfn(0, ch.nn[0]);
+    double rprev = wsum(0), rcur = rprev, eps = 0.0;
+    it.lval = it.val = it.weight * rprev;
+    if (ch.nlev > 1) {
+        for (int l = 1; l < ch.nlev; l++) {
+            evalfn(ch.nn[l - 1], ch.nn[l]);
+            if (l > 1) rprev = rcur;
+            rcur = wsum(l);
+            eps = fabs(rcur - rprev);
+            if (fabs(rcur) < MQ_ZTOL || fabs(eps / rcur) < MI_GOAL) break;
+        }
+        it.lval = it.weight * rprev;
+        it.val = it.weight * rcur;
+        it.err = it.weight * eps;
+    }
+}
+template <int NB>
+__device__ void mq_quadrature(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ], MqItem<NB> &it, double *f) {
+    mq_chain<NB>(v, xv, qv, c_method.main, it, f);
+    if (c_method.main.nlev == 1 && c_method.has_err) {      // no extension: the error rule gives the better value and the error
+        const double temp = it.val;
+        mq_chain<NB>(v, xv, qv, c_method.err, it, f);
+        it.lval = temp;
+        it.err = fabs(it.val - temp);
+    }
+}
+
+// integrator_integrate (integrate.c:2759-2835): a binary heap of work items ordered by error estimate; the worst item is
+// subdivided until the summed error is below the goal.  `heap` holds `cap` items; *overflow is set when that is not enough.
+template <int NB>
+__device__ double mq_integrate(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ], MqItem<NB> *heap, int cap, bool &overflow) {
+    constexpr int NSUB = NB == 2 ? 2 : (NB == 3 ? 4 : 8), NPTS = NB == 2 ? 1 : (NB == 3 ? 3 : 6);
+    double f[MQ_MAXNODES];
+    int count = 0;
+    auto push = [&](const MqItem<NB> &w) {                   // integrator_pushworkitem
+        heap[count++] = w;
+        for (int i = count - 1, p; i > 0; i = p) {
+            p = (i - 1) / 2;
+            if (heap[i].err > heap[p].err) { MqItem<NB> t = heap[i]; heap[i] = heap[p]; heap[p] = t; } else break;
+        }
+    };
+    auto pop = [&](MqItem<NB> &w) {                          // integrator_popworkitem
+        w = heap[0];
+        const int n = count - 1;
+        if (n > 0) heap[0] = heap[n];
+        count--;
+        for (int i = 0, p, q; i < n; i = p) {
+            p = 2 * i + 1; q = p + 1;
+            if (q < n && heap[q].err > heap[p].err) p = q;
+            if (p < n && heap[p].err > heap[i].err) { MqItem<NB> t = heap[i]; heap[i] = heap[p]; heap[p] = t; } else break;
+        }
+    };
+    double val = 0.0, errest = 0.0;
+    auto estimate = [&]() {                                  // integrator_estimate: Kahan sums over the heap, last entry first
+        double sv = 0.0, cv = 0.0, se = 0.0, ce = 0.0;
+        for (int i = count - 1; i >= 0; i--) {
+            const double yv = heap[i].val - cv, ye = heap[i].err - ce;
+            const double tv = sv + yv, te = se + ye;
+            cv = (tv - sv) - yv; ce = (te - se) - ye;
+            sv = tv; se = te;
+        }
+        val = sv; errest = se;
+    };
+    MqItem<NB> work;
+    work.weight = 1.0; work.val = work.lval = work.err = 0.0;
+    for (int i = 0; i < NB * NB; i++) work.v[i] = (i % (NB + 1) == 0) ? 1.0 : 0.0;
+    mq_quadrature<NB>(v, xv, qv, work, f);
+    push(work);
+    estimate();
+    if (c_method.adapt)
+        for (int it = 0; it <= MQ_MAXIT; it++) {
+            if (fabs(val) < MQ_ZTOL || fabs(errest / val) < MI_GOAL) break;
+            if (count - 1 + NSUB > cap) { overflow = true; break; }
+            pop(work);
+            // integrator_subdivide: midpoints in the coordinates of the root element
+            double P[NB + NPTS][NB];
+            for (int k = 0; k < NB; k++) for (int j = 0; j < NB; j++) P[k][j] = work.v[k * NB + j];
+            if (NB == 2) { for (int j = 0; j < NB; j++) P[2][j] = 0.5 * P[0][j] + 0.5 * P[1][j]; }
+            else if (NB == 3) {
+                for (int j = 0; j < NB; j++) {
+                    P[3][j] = 0.5 * P[0][j] + 0.5 * P[1][j] + 0.0 * P[2][j];
+                    P[4][j] = 0.0 * P[0][j] + 0.5 * P[1][j] + 0.5 * P[2][j];
+                    P[5][j] = 0.5 * P[0][j] + 0.0 * P[1][j] + 0.5 * P[2][j];
+                }
+            } else {
+                const int pair[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+                for (int m = 0; m < 6; m++) for (int j = 0; j < NB; j++) {
+                    double s = 0.0;
+                    for (int k = 0; k < 4; k++) s += ((k == pair[m][0] || k == pair[m][1]) ? 0.5 : 0.0) * P[k][j];
+                    P[4 + m][j] = s;
+                }
+            }
+            MqItem<NB> kid[NSUB];
+            bool bad = false;
+            for (int c = 0; c < NSUB; c++) {
+                kid[c].val = kid[c].lval = kid[c].err = 0.0;
+                kid[c].weight = work.weight * (1.0 / NSUB);
+                if (kid[c].weight < val * MCU_EPS) bad = true;         // IntgrtrSbdvsns: the reference gives up with an error
+                for (int k = 0; k < NB; k++) {
+                    const int src = NB == 2 ? c_sub_line[c][k] : (NB == 3 ? c_sub_tri[c][k] : c_tetsub[c][k]);
+                    for (int j = 0; j < NB; j++) kid[c].v[k * NB + j] = P[src][j];
+                }
+            }
+            if (bad) { overflow = true; break; }
+            for (int c = 0; c < NSUB; c++) mq_quadrature<NB>(v, xv, qv, kid[c], f);
+            // integrator_sharpenerrorestimate (Laurie, BIT 23 (1983) 258)
+            double a2 = 0.0, b2 = 0.0;
+            for (int c = 0; c < NSUB; c++) { a2 += kid[c].val; b2 += kid[c].lval; }
+            const double a1 = work.val, b1 = work.lval;
+            if (fabs(a2 - a1) < fabs(b2 - b1) && fabs(a2 - b2) < fabs(a1 - b1)) {
+                const double sigma = fabs((a2 - a1) / (b2 - b1 - a2 + a1));
+                for (int c = 0; c < NSUB; c++) kid[c].err *= sigma;
+            }
+            // integrator_update
+            double dval = 0.0, derr = 0.0;
+            val -= work.val; errest -= work.err;
+            for (int c = 0; c < NSUB; c++) { dval += kid[c].val; derr += kid[c].err; push(kid[c]); }
+            val += dval; errest += derr;
+        }
+    estimate();
+    return val;
+}
+
+// items a thread keeps in local memory (16 KB): enough for 255 / 52 / 14 subdivisions
+#define MQ_CAP_LINE 256
+#define MQ_CAP_TRI 157
+#define MQ_CAP_TET 102
+__device__ double mi_method(const MiView &v, const double (*xv)[3], const double (*qv)[MI_MAXQ]) {
+    bool overflow = false;
+    double r;
+    double raw[2048];                  // one buffer for the three item types (all doubles): 256 x 8, 157 x 13, 102 x 20 <= 2048
+    static_assert(sizeof(MqItem<2>) * MQ_CAP_LINE <= sizeof(raw) && sizeof(MqItem<3>) * MQ_CAP_TRI <= sizeof(raw) && sizeof(MqItem<4>) * MQ_CAP_TET <= sizeof(raw), "heap buffer");
+    if (v.g == 1) r = mq_integrate<2>(v, xv, qv, reinterpret_cast<MqItem<2> *>(raw), MQ_CAP_LINE, overflow);
+    else if (v.g == 2) r = mq_integrate<3>(v, xv, qv, reinterpret_cast<MqItem<3> *>(raw), MQ_CAP_TRI, overflow);
+    else r = mq_integrate<4>(v, xv, qv, reinterpret_cast<MqItem<4> *>(raw), MQ_CAP_TET, overflow);
+    if (overflow && v.fail) atomicOr(v.fail, 1u);
+    return r;
+}
+
 // tangent() / normal() / grad(q) of the element (integral_evaluatetangent, integral_evaluatenormal,
 // integral_evaluategradient → gradsq_evaluategradient; functional.c:4402-4425, 4444-4470, 4716-4726)
 __device__ __forceinline__ void mi_derive(const MiView &v, const double (*xv)[3], double (*qv)[MI_MAXQ]) {
@@ -278,14 +458,14 @@ __device__ __forceinline__ double mi_element(const MiView &v, const double (*xv)
     if (v.nq > v.nq_in) mi_derive(v, xv, qv);
     double val, size;
     if (v.g == 1) {
-        val = mi_line(v, xv, qv);
+        val = v.method ? mi_method(v, xv, qv) : mi_line(v, xv, qv);
         double s[3] = {xv[1][0] - xv[0][0], xv[1][1] - xv[0][1], xv[1][2] - xv[0][2]};
         size = sqrt(dot3(s, s));
     } else if (v.g == 2) {
-        val = mi_tri(v, xv, qv);
+        val = v.method ? mi_method(v, xv, qv) : mi_tri(v, xv, qv);
         size = area_of(xv);
     } else {
-        val = mi_tet(v, xv, qv);
+        val = v.method ? mi_method(v, xv, qv) : mi_tet(v, xv, qv);
         size = volume_of(xv);
     }
     return val * size;
@@ -435,8 +615,69 @@ static void make_rules(MiRules &R) {
 }
 
 // arguments shared by mcu_integral and mcu_integral_gradient: validates, uploads the rules and the program, fills the view
+// integrator_configure + the upload of the configured chains (c_method)
+static bool fill_chain(const McuQuadRules &Q, int rule, MqChain &ch) {
+    memset(&ch, 0, sizeof(ch));
+    const int nb = Q.rules[rule].grade + 1;
+    int woff = 0, last = rule;
+    for (int r = rule; r >= 0; r = Q.rules[r].ext) {
+        if (ch.nlev == MQ_MAXLEV) return false;
+        const McuQuadRule &R = Q.rules[r];
+        const int nw = std::max(R.nnodes, (int) R.weights.size());
+        if (R.nnodes > MQ_MAXNODES || woff + nw > MQ_MAXW) return false;
+        ch.nn[ch.nlev] = R.nnodes; ch.woff[ch.nlev] = woff;
+        for (int i = 0; i < R.nnodes; i++) ch.w[woff + i] = R.weights[i];
+        woff += R.nnodes;
+        ch.nlev++;
+        last = r;
+    }
+    const std::vector<double> &nodes = Q.families[Q.rules[last].family];
+    for (int i = 0; i < Q.rules[last].nnodes * nb; i++) ch.nodes[i] = nodes[i];
+    return true;
+}
+
+static int method_setup(int grade, const mcu_quad_method *method, cudaStream_t st) {
+    const McuQuadRules &Q = McuQuadRules::get();
+    int rule = -1, errrule = -1;
+    char name[sizeof(method->rule) + 1];
+    memcpy(name, method->rule, sizeof(method->rule));
+    name[sizeof(method->rule)] = 0;
+    if (!Q.configure(grade, method->adapt != 0, method->degree, name, rule, errrule)) {
+        mcu_set_error("no quadrature rule '%s' / degree %d for grade %d (the reference raises IntgrtrRlNtFnd / IntgrtrRlUnavlb)", name, method->degree, grade);
+        return MCU_ERR_UNSUPPORTED;
+    }
+    static MqMethod M;                          // pinned for the asynchronous copy below
+    memset(&M, 0, sizeof(M));
+    M.adapt = method->adapt != 0;
+    M.has_err = errrule >= 0;
+    if (!fill_chain(Q, rule, M.main) || (errrule >= 0 && !fill_chain(Q, errrule, M.err))) { mcu_set_error("quadrature rule chain too long"); return MCU_ERR_UNSUPPORTED; }
+    if (cudaMemcpyToSymbolAsync(c_method, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return MCU_ERR_CUDA;
+    return MCU_OK;
+}
+
+extern "C" int mcu_debug_quadrule(int index, char name[32], int info[5], double *nodes, double *weights, int cap) {
+    const McuQuadRules &Q = McuQuadRules::get();
+    if (index < 0 || index >= (int) Q.rules.size()) return MCU_ERR_ARGS;
+    const McuQuadRule &R = Q.rules[index];
+    if (name) { memset(name, 0, 32); strncpy(name, R.name.c_str(), 31); }
+    if (info) { info[0] = R.grade; info[1] = R.order; info[2] = R.nnodes; info[3] = R.ext; info[4] = (int) R.weights.size(); }
+    const int nb = R.grade + 1;
+    if (nodes) for (int i = 0; i < R.nnodes * nb && i < cap; i++) nodes[i] = Q.families[R.family][i];
+    if (weights) for (int i = 0; i < (int) R.weights.size() && i < cap; i++) weights[i] = R.weights[i];
+    return MCU_OK;
+}
+
+extern "C" int mcu_debug_quadconfigure(int grade, int adapt, int degree, const char *name, int out[2]) {
+    int rule, err;
+    if (!McuQuadRules::get().configure(grade, adapt != 0, degree, name, rule, err)) return MCU_ERR_UNSUPPORTED;
+    out[0] = rule; out[1] = err;
+    return MCU_OK;
+}
+
+static unsigned *g_integral_fail = nullptr;     // device word: an element ran out of work items (rule-table integrator)
+
 static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
-                          mcu_selection *sel, MiView &v, cudaStream_t st) {
+                          mcu_selection *sel, MiView &v, cudaStream_t st, const mcu_quad_method *method = nullptr) {
     if (!m || (grade < 1 || grade > 3) || nops < 1 || nops > MI_MAXOPS || !prog || nfields < 0) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
     if (!m->conn[grade].present) { mcu_set_error("mesh has no elements of grade %d", grade); return MCU_ERR_ELNOTFOUND; }
     if (sel && (sel->m != m || sel->g != grade)) { mcu_set_error("selection does not belong to this mesh / grade"); return MCU_ERR_ARGS; }
@@ -448,6 +689,13 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
         rules_up = true;
     }
     memset(&v, 0, sizeof(v));
+    if (method) {
+        int rm = method_setup(grade, method, st);
+        if (rm) return rm;
+        if (!g_integral_fail && cudaMalloc((void **) &g_integral_fail, sizeof(unsigned)) != cudaSuccess) return MCU_ERR_ALLOC;
+        if (cudaMemsetAsync(g_integral_fail, 0, sizeof(unsigned), st) != cudaSuccess) return MCU_ERR_CUDA;
+        v.method = 1; v.fail = g_integral_fail;
+    }
     v.dim = m->dim; v.g = grade; v.nops = nops; v.nel = m->conn[grade].nel;
     v.vert = m->d_vert; v.rix = m->conn[grade].d_rix;
     if (sel) { int rs = mcu_ensure_selection(sel); if (rs) return rs; }
@@ -616,12 +864,27 @@ extern "C" int mcu_pointwise(mcu_mesh *m, int nprog, const int *nops, const mcu_
  * fieldgradient are functional_mapnumericalgradient / functional_mapnumericalfieldgradient over the quadrature,
  * functional.c:5240, 5319-5340, 5434-5458).  wrt < 0: vertex positions, host_out nv * dim doubles; wrt = k: the k-th
  * field, host_out nv * psize_k doubles (the layout of that Field's store). */
+// after the kernels of a rule-table evaluation: did any element run out of work items (or hit the reference's
+// IntgrtrSbdvsns condition)?  Such a call is handed back to the reference.
+static int method_check(const MiView &v, cudaStream_t st) {
+    if (!v.method) return MCU_OK;
+    unsigned f = 0;
+    if (cudaMemcpyAsync(&f, v.fail, sizeof(unsigned), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return MCU_ERR_CUDA;
+    if (f) { mcu_set_error("rule-table integrator: an element needs more subdivisions than the device keeps (or cannot be subdivided further)"); return MCU_ERR_UNSUPPORTED; }
+    return MCU_OK;
+}
+
 extern "C" int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                                      mcu_selection *sel, int wrt, double *host_out) {
+    return mcu_integral_gradient_method(m, grade, nops, prog, nfields, fields, sel, wrt, nullptr, host_out);
+}
+
+extern "C" int mcu_integral_gradient_method(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                                            mcu_selection *sel, int wrt, const mcu_quad_method *method, double *host_out) {
     if (!host_out || wrt >= nfields) { mcu_set_error("bad integral gradient arguments"); return MCU_ERR_ARGS; }
     cudaStream_t st = mcu_stream();
     MiView v;
-    int rc = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st);
+    int rc = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st, method);
     if (rc) return rc;
     int qbase = -1, ncomp = m->dim;
     if (wrt >= 0) {
@@ -652,6 +915,7 @@ extern "C" int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * no, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { mcu_set_error("integral gradient failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
+    if (rc == MCU_OK) rc = method_check(v, st);
     cudaFree(d_scratch);
     cudaFree(d_out);
     return rc;
@@ -659,10 +923,15 @@ extern "C" int mcu_integral_gradient(mcu_mesh *m, int grade, int nops, const mcu
 
 extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
                             mcu_selection *sel, int mode, double *host_out) {
+    return mcu_integral_method(m, grade, nops, prog, nfields, fields, sel, mode, nullptr, host_out);
+}
+
+extern "C" int mcu_integral_method(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,
+                                   mcu_selection *sel, int mode, const mcu_quad_method *method, double *host_out) {
     if (!host_out || (mode != MCU_TOTAL && mode != MCU_INTEGRAND)) { mcu_set_error("bad integral arguments"); return MCU_ERR_ARGS; }
     cudaStream_t st = mcu_stream();
     MiView v;
-    int rc0 = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st);
+    int rc0 = integral_setup(m, grade, nops, prog, nfields, fields, sel, v, st, method);
     if (rc0) return rc0;
     double *d_int = nullptr, *d_tot = nullptr;
     CompSum *d_part = nullptr;
@@ -684,6 +953,7 @@ extern "C" int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op 
     } else if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_int, sizeof(double) * nel, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { mcu_set_error("integral failed: %s", cudaGetErrorString(e)); rc = MCU_ERR_CUDA; }
+    if (rc == MCU_OK) rc = method_check(v, st);
     cudaFree(d_int);
     if (d_part) cudaFree(d_part);
     if (d_tot) cudaFree(d_tot);

@@ -40,6 +40,7 @@
 #include "selection.h"
 #include "field.h"
 #include "functional.h"
+#include "integrate.h"
 
 #include <math.h>
 
@@ -612,8 +613,8 @@ MC_EVENEER(integrand, MCU_INTEGRAND)
 MC_EVENEER(gradient, MCU_GRADIENT)
 
 /* LineIntegral / AreaIntegral / VolumeIntegral (functional.c:5186-5243, 5371-5426, 5471-5546).  The integrand closure is
- * translated into a postfix program (mc_translate.h); what cannot be translated — and method dictionaries, reference
- * meshes, fields on finite-element spaces — goes to the reference builtin. */
+ * translated into a postfix program (mc_translate.h); what cannot be translated — and reference meshes, fields on
+ * finite-element spaces — goes to the reference builtin.  A `method` dictionary selects the rule-table integrator. */
 #define MC_MAXPROG 256
 static long mc_stat_translated = 0;
 static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, value *out) {
@@ -628,7 +629,24 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     value fn = MORPHO_NIL, val = MORPHO_NIL;
     int wrt = -1;
     if (!prop(self, SCALARPOTENTIAL_FUNCTION_PROPERTY, &fn)) return false;
-    if (prop(self, INTEGRAL_METHOD_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;            /* new integrator */
+    /* a `method` dictionary selects the rule-table integrator (integrator_configurewithdictionary, integrate.c:2706-2751):
+     * "rule" (String), "degree" (Int), "adapt" (Bool); an entry of the wrong type is the reference's error to raise */
+    mcu_quad_method qm, *method = NULL;
+    if (prop(self, INTEGRAL_METHOD_PROPERTY, &val) && !MORPHO_ISNIL(val)) {
+        if (!MORPHO_ISDICTIONARY(val)) return false;
+        objectdictionary *md = MORPHO_GETDICTIONARY(val);
+        memset(&qm, 0, sizeof(qm));
+        qm.adapt = 1; qm.degree = -1;
+        objectstring krule = MORPHO_STATICSTRING(INTEGRATE_RULELABEL), kdeg = MORPHO_STATICSTRING(INTEGRATE_DEGREELABEL), kadapt = MORPHO_STATICSTRING(INTEGRATE_ADAPTLABEL);
+        value e;
+        if (dictionary_get(&md->dict, MORPHO_OBJECT(&krule), &e)) {
+            if (!MORPHO_ISSTRING(e) || strlen(MORPHO_GETCSTRING(e)) >= sizeof(qm.rule)) return false;
+            strcpy(qm.rule, MORPHO_GETCSTRING(e));
+        }
+        if (dictionary_get(&md->dict, MORPHO_OBJECT(&kdeg), &e)) { if (!MORPHO_ISINTEGER(e)) return false; qm.degree = MORPHO_GETINTEGERVALUE(e); }
+        if (dictionary_get(&md->dict, MORPHO_OBJECT(&kadapt), &e)) { if (!MORPHO_ISBOOL(e)) return false; qm.adapt = MORPHO_GETBOOLVALUE(e) ? 1 : 0; }
+        method = &qm;
+    }
     if (prop(self, LINEARELASTICITY_REFERENCE_PROPERTY, &val) && !MORPHO_ISNIL(val)) return false;
     if (prop(self, LINEARELASTICITY_WTBYREF_PROPERTY, &val) && MORPHO_ISTRUE(val)) return false;
     objectfield *flds[16];
@@ -678,22 +696,22 @@ static bool mc_eval_integral(vm *v, int nargs, value *args, grade g, int mode, v
     double total = 0.0;
     objectmatrix *new = NULL;
     objectfield *newf = NULL;
-    if (mode == MCU_TOTAL) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_TOTAL, &total);
+    if (mode == MCU_TOTAL) rc = mcu_integral_method(mr->m, g, nops, prog, nf, df, sel, MCU_TOTAL, method, &total);
     else if (mode == MCU_INTEGRAND) {
         objectsparse *s = mesh_getconnectivityelement(info.mesh, 0, g);
         new = matrix_new(1, (MatrixIdx_t) s->ccs.ncols, false);
         if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
-        else if (s->ccs.ncols > 0) rc = mcu_integral(mr->m, g, nops, prog, nf, df, sel, MCU_INTEGRAND, new->elements);
+        else if (s->ccs.ncols > 0) rc = mcu_integral_method(mr->m, g, nops, prog, nf, df, sel, MCU_INTEGRAND, method, new->elements);
         else rc = MCU_OK;
     } else if (mode == MCU_GRADIENT) {
         new = matrix_new(mr->dim, mr->nv, false);
         if (!new) { morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
-        else rc = mcu_integral_gradient(mr->m, g, nops, prog, nf, df, sel, -1, new->elements);
+        else rc = mcu_integral_gradient_method(mr->m, g, nops, prog, nf, df, sel, -1, method, new->elements);
     } else {
         objectfield *w = flds[wrt];
         newf = object_newfield(info.mesh, w->prototype, w->fnspc, w->dof);           /* functional.c:1449 */
         if (!newf || newf->data.nels != w->data.nels) { if (newf) object_free((object *) newf); newf = NULL; morpho_runtimeerror(v, ERROR_ALLOCATIONFAILED); rc = -1; }
-        else rc = mcu_integral_gradient(mr->m, g, nops, prog, nf, df, sel, wrt, newf->data.elements);
+        else rc = mcu_integral_gradient_method(mr->m, g, nops, prog, nf, df, sel, wrt, method, newf->data.elements);
     }
     if (sel) mcu_selection_destroy(sel);
     if (rc == MCU_OK) {

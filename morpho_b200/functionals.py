@@ -262,6 +262,11 @@ class PairwisePotential:
         return self._run(mesh, MCU_GRADIENT, mesh.nv * mesh.dim).reshape(mesh.nv, mesh.dim)
 
 
+class _QuadMethod(C.Structure):
+    """mcu_quad_method (include/morpho_cuda.h)"""
+    _fields_ = [("adapt", C.c_int), ("degree", C.c_int), ("rule", C.c_char * 32)]
+
+
 class _Integral:
     """LineIntegral / AreaIntegral (functional.c:5186-5243, 5371-5426): the integral over every element of a callable
     of the position and of the interpolated field values, by the reference's default adaptive quadrature
@@ -271,10 +276,19 @@ class _Integral:
     (functional_mapnumericalgradient / functional_mapnumericalfieldgradient, functional.c:1142-1247, 1305-1503)."""
     grade = 0
 
-    def __init__(self, fn, *fields):
+    def __init__(self, fn, *fields, method=None):
         self.fn = fn
         self.fields = list(fields)
         self._prog = None
+        # method = None: the default integrator; a dict ({} included) selects the rule-table integrator like the
+        # reference's `method` option (integrator_configurewithdictionary, integrate.c:2706-2751): "rule", "degree", "adapt"
+        self.method = None
+        if method is not None:
+            unknown = set(method) - {"rule", "degree", "adapt"}
+            if unknown:
+                raise MorphoError(_lib.MCU_ERR_ARGS, "IntgrtrMthdTyp", f"unknown method entries {sorted(unknown)}")
+            self.method = _QuadMethod(1 if method.get("adapt", True) else 0, int(method.get("degree", -1)),
+                                      str(method.get("rule", "")).encode())
 
     def program(self, dim):
         if self._prog is None or self._prog[0] != dim:
@@ -291,7 +305,8 @@ class _Integral:
         out = np.zeros(max(nel, 1) if mode == MCU_INTEGRAND else 1, dtype=np.float64)
         fh = (C.c_void_p * max(len(self.fields), 1))(*[f._h for f in self.fields])
         hsel = sel._handle(self.grade) if sel is not None else None
-        check(lib().mcu_integral(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, mode, out.ctypes.data))
+        mref = C.byref(self.method) if self.method is not None else None
+        check(lib().mcu_integral_method(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, mode, mref, out.ctypes.data))
         return out[:nel] if mode == MCU_INTEGRAND else out
 
     def total(self, *args):
@@ -309,7 +324,8 @@ class _Integral:
         out = np.zeros((mesh.nv, ncomp), dtype=np.float64)
         fh = (C.c_void_p * max(len(self.fields), 1))(*[f._h for f in self.fields])
         hsel = sel._handle(self.grade) if sel is not None else None
-        check(lib().mcu_integral_gradient(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, wrt, out.ctypes.data))
+        mref = C.byref(self.method) if self.method is not None else None
+        check(lib().mcu_integral_gradient_method(mesh._h, self.grade, len(prog), prog.ctypes.data, len(self.fields), fh, hsel, wrt, mref, out.ctypes.data))
         return out
 
     def gradient(self, *args):

@@ -1,2 +1,2 @@
 set -x
-( time python -m pytest tests/test_extension.py -m gpu -x -q -k "connectivity" > gpurun_out/pytest_new.log 2>&1 ); echo "pytest rc=$?"; tail -25 gpurun_out/pytest_new.log | cut -c1-1200
+( time python -m pytest tests/test_integral.py tests/test_extension.py -m gpu -x -q -k "not reference_suite and not tactoid and not catenoid_example and not thomson" > gpurun_out/pytest_new.log 2>&1 ); echo "pytest rc=$?"; tail -30 gpurun_out/pytest_new.log | cut -c1-900

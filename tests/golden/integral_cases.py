@@ -78,6 +78,35 @@ CASES = [
 ] + VOLUME_CASES
 
 
+# The rule-table integrator (`method` dictionary): name, base case, Morpho source of the dictionary, the same as a Python dict.
+# Covers the default rule of every grade, rules by name with an extension chain, a rule whose error estimate comes from
+# a second rule (keast4 -> keast5), selection by degree, and adapt = false.
+METHOD_CASES = [
+    ("m_line_default", "line_osc", "{}", {}),
+    ("m_line_gauss7", "line_sqrt", '{ "rule" : "gauss7" }', {"rule": "gauss7"}),
+    ("m_line_gauss1", "line_osc", '{ "rule" : "gauss1" }', {"rule": "gauss1"}),
+    ("m_line_degree", "line_field", '{ "degree" : 6 }', {"degree": 6}),
+    ("m_line_noadapt", "line_poly", '{ "rule" : "gauss2", "adapt" : false }', {"rule": "gauss2", "adapt": False}),
+    ("m_line_sel", "line_sel", "{}", {}),
+    ("m_area_default", "area_osc", "{}", {}),
+    ("m_area_peak", "area_peak", "{}", {}),
+    ("m_area_tri4", "area_quad", '{ "rule" : "tri4" }', {"rule": "tri4"}),
+    ("m_area_cubtri19", "area_field", '{ "rule" : "cubtri19" }', {"rule": "cubtri19"}),
+    ("m_area_gm", "area_osc", '{ "rule" : "grundmann2d2" }', {"rule": "grundmann2d2"}),
+    ("m_area_degree", "area_anchor", '{ "degree" : 4 }', {"degree": 4}),
+    ("m_area_noadapt", "area_gradsq", '{ "rule" : "cubtri7", "adapt" : false }', {"rule": "cubtri7", "adapt": False}),
+    ("m_vol_default", "vol_poly", "{}", {}),
+    ("m_vol_osc", "vol_osc", "{}", {}),
+    ("m_vol_keast4", "vol_field", '{ "rule" : "keast4" }', {"rule": "keast4"}),
+    ("m_vol_tet5", "vol_osc", '{ "rule" : "tet5" }', {"rule": "tet5"}),
+    ("m_vol_gm3", "vol_gradsq", '{ "rule" : "grundmann3d3" }', {"rule": "grundmann3d3"}),
+    ("m_vol_degree", "vol_sel", '{ "degree" : 5 }', {"degree": 5}),
+]
+# gradients through the rule-table integrator: (method case, wrt)
+METHOD_GRAD_CASES = [("m_line_default", -1), ("m_line_degree", 1), ("m_area_default", -1), ("m_area_cubtri19", 0), ("m_vol_keast4", -1),
+                     ("m_vol_keast4", 1)]
+
+
 def fields_for(vert):
     return _fields(vert)
 

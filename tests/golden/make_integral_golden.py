@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 from morpho_b200 import meshgen as mg  # noqa: E402
 from morpho_b200.integrand import trace  # noqa: E402
 from oracle.oracle import Reference  # noqa: E402
-from tests.golden.integral_cases import CASES, FIELD_SRC, GRAD_CASES, POT_CASES, fields_for, meshes  # noqa: E402
+from tests.golden.integral_cases import CASES, FIELD_SRC, GRAD_CASES, METHOD_CASES, METHOD_GRAD_CASES, POT_CASES, fields_for, meshes  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref")
 
@@ -61,6 +61,34 @@ def vm_integrands(tmp, ms):
             src.append(f'for (i in 0...d_{key}[1]) for (k in 0...d_{key}[0]) print g_{key}[k,i].format("%.17g")')
         else:
             src.append(f"var g_{key} = {cls}({closure}{fargs}).fieldgradient({flds[wrt]}_{mesh}, m_{mesh}{selarg})")
+            src.append(f'for (x in g_{key}) {{ if (ismatrix(x)) {{ for (y in x) print y.format("%.17g") }} else print x.format("%.17g") }}')
+    CLS = {1: "LineIntegral", 2: "AreaIntegral", 3: "VolumeIntegral"}
+    bymethod = {m[0]: m for m in METHOD_CASES}
+    for mname, base, msrc, _ in METHOD_CASES:
+        name, mesh, grade, _, closure, flds, sel = bycase[base]
+        fargs = "".join(f", {f}_{mesh}" for f in flds)
+        selarg = ""
+        if sel is not None:
+            src.append(f"var s_{mname} = Selection(m_{mesh})")
+            for i in sel:
+                src.append(f"s_{mname}[{grade},{i}] = true")
+            selarg = f", s_{mname}"
+        src.append(f"var f_{mname} = {CLS[grade]}({closure}{fargs}, method={msrc})")
+        src.append(f"var r_{mname} = f_{mname}.integrand(m_{mesh}{selarg})")
+        src.append(f'print "@{mname}"')
+        src.append(f'for (i in 0...r_{mname}.dimensions()[1]) print r_{mname}[0,i].format("%.17g")')
+    for mname, wrt in METHOD_GRAD_CASES:
+        base = bymethod[mname][1]
+        name, mesh, grade, _, closure, flds, sel = bycase[base]
+        key = f"grad__{mname}__{'x' if wrt < 0 else wrt}"
+        selarg = f", s_{mname}" if sel is not None else ""
+        src.append(f'print "@{key}"')
+        if wrt < 0:
+            src.append(f"var g_{key} = f_{mname}.gradient(m_{mesh}{selarg})")
+            src.append(f"var d_{key} = g_{key}.dimensions()")
+            src.append(f'for (i in 0...d_{key}[1]) for (k in 0...d_{key}[0]) print g_{key}[k,i].format("%.17g")')
+        else:
+            src.append(f"var g_{key} = f_{mname}.fieldgradient({flds[wrt]}_{mesh}, m_{mesh}{selarg})")
             src.append(f'for (x in g_{key}) {{ if (ismatrix(x)) {{ for (y in x) print y.format("%.17g") }} else print x.format("%.17g") }}')
     for name, mesh, _, gradf, fsrc, gsrc, sel in POT_CASES:
         src.append(f"var p_{name} = ScalarPotential({fsrc}{', ' + gsrc if gsrc else ''})")
@@ -119,6 +147,13 @@ def main():
         assert err < 1e-13, name
     for gname, wrt in GRAD_CASES:
         key = f"grad__{gname}__{'x' if wrt < 0 else wrt}"
+        store[key] = vm[key]
+        print(f"{key:28s} n={vm[key].size:5d} |g|={np.linalg.norm(vm[key]):.15e}")
+    for mname, base, _, _ in METHOD_CASES:
+        store[mname] = vm[mname]
+        print(f"{mname:18s} n={vm[mname].size:5d} sum={vm[mname].sum():+.15e}  (default integrator on the same case: {store[base].sum():+.15e})")
+    for mname, wrt in METHOD_GRAD_CASES:
+        key = f"grad__{mname}__{'x' if wrt < 0 else wrt}"
         store[key] = vm[key]
         print(f"{key:28s} n={vm[key].size:5d} |g|={np.linalg.norm(vm[key]):.15e}")
     for name, *_ in POT_CASES:

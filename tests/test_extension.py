@@ -144,12 +144,14 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 59 and evals >= 59 and fallbacks == 1, (stats, err)    # 30 values + 22 gradients + 7 potentials; 1 untranslatable
+    assert translated == 73 and evals >= 73 and fallbacks == 1, (stats, err)    # 30 values + 22 gradients + 7 potentials + 14 with a method dictionary; 1 untranslatable
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
     cut2 = ref.index("-- potentials")
     compare(ref[cut:cut2], new[cut:cut2], 2e-9)   # finite differences: round-off of f amplified by 1/(2 eps)
-    compare(ref[cut2:], new[cut2:-1], 1e-9)       # potentials: exact gradient function 1e-12-ish, FD variant 1e-10
+    cut3 = ref.index("-- methods")
+    compare(ref[cut2:cut3], new[cut2:cut3], 1e-9) # potentials: exact gradient function 1e-12-ish, FD variant 1e-10
+    compare(ref[cut3:], new[cut3:-1], 1e-12)      # the rule-table integrator (method dictionaries)
 
 
 @pytest.mark.gpu
@@ -178,10 +180,14 @@ def test_volume_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 32 and fallbacks == 0, (stats, err)      # 18 values + 14 gradients
+    # 18 values + 14 gradients + 8 with a method dictionary; an integrand whose elements need more work items than the
+    # device keeps per element (keast4 on the oscillating one) is handed back to the reference builtin: <= 2 such calls
+    assert translated == 40 and fallbacks <= 2, (stats, err)
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
-    compare(ref[cut:], new[cut:-1], 2e-9)
+    cut2 = ref.index("-- methods")
+    compare(ref[cut:cut2], new[cut:cut2], 2e-9)
+    compare(ref[cut2:], new[cut2:-1], 1e-12)
 
 
 @pytest.mark.gpu
