@@ -131,6 +131,14 @@ int mcu_mesh_addgrade(mcu_mesh *m, int grade, int *nel_out);
  * *grade_out = that grade, *n_out = their number; at most cap ids are copied to host_ids (may be NULL to count). */
 int mcu_mesh_boundary(mcu_mesh *m, int *grade_out, int *n_out, int *host_ids, int cap);
 int mcu_mesh_get_connectivity(mcu_mesh *m, int grade, int *host_rix);
+/* conn(row, col), 1 <= row < col <= 3, the grade-LOWERING matrix (mesh_addlowermatrix, mesh.c:621-660): for every element
+ * of grade col the ids, ascending, of the elements of grade row all of whose vertices it contains, in compressed
+ * columns.  host_cptr: nel(col) + 1 ints; host_rix: room for nel(col) * C(col+1, row+1) ints; *nnz_out = entries
+ * written; *nrows_out / *ncols_out = largest row / column index with an entry, plus one (the size the reference's
+ * dictionary-of-keys matrix grows to: trailing elements without entries are not part of it).  The
+ * grade-RAISING matrices are transposes (mesh_addconnectivityelement, mesh.c:663-685: sparse_transpose).
+ * MCU_ERR_UNSUPPORTED when two elements of grade row have the same vertices. */
+int mcu_mesh_lower(mcu_mesh *m, int row, int col, int *host_cptr, int *host_rix, int *nnz_out, int *nrows_out, int *ncols_out);
 /* vertex→element incidence as the reference builds it with sparse_transpose → cs_transpose
  * (sparse.c:1227-1244, mesh.c:663-685): tptr[nv+1], tidx[nel*(g+1)] element ids ascending per vertex. */
 int mcu_mesh_get_transpose(mcu_mesh *m, int grade, int *host_tptr, int *host_tidx);

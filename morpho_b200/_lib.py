@@ -74,6 +74,7 @@ def lib():
         "mcu_mesh_drop_connectivity": (C.c_int, [vp, C.c_int]),
         "mcu_mesh_addgrade": (C.c_int, [vp, C.c_int, ip]),
         "mcu_mesh_boundary": (C.c_int, [vp, ip, ip, vp, C.c_int]),
+        "mcu_mesh_lower": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, ip, ip, ip]),
         "mcu_integral": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp]),
         "mcu_debug_patch_triangles": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
         "mcu_pointwise": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp]),

@@ -1,4 +1,4 @@
-// mcu_connect.cu — connectivity construction on the device: Mesh.addgrade.
+// mcu_connect.cu — connectivity construction on the device: Mesh.addgrade, the boundary selection, grade-lowering matrices.
 //
 // mesh_addgrade (mesh.c:419-489) walks the elements of the next higher grade in id order, generates for each the
 // (g+1)-subsets of its vertices in lexicographic counter order and keeps the subsets not seen before (an n-tuple hash,
@@ -248,6 +248,141 @@ done:
     if (pos) cudaFree(pos);
     if (tmp) cudaFree(tmp);
     if (d_ids) cudaFree(d_ids);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// Grade-lowering connectivity conn(row, col), 1 <= row < col (mesh_addlowermatrix, mesh.c:621-660): for every element of
+// grade col the elements of grade row all of whose vertices it contains.  The reference merges the incidence lists of
+// the element's vertices, sorts them and counts repeats (mesh_matchelements, mesh.c:584-617), then inserts the
+// matches into a dictionary-of-keys matrix; here the elements of grade row are sorted by their vertex tuple once and
+// every (element, subset) looks its tuple up by binary search.  Columns come out with ascending ids, as the
+// reference's conversion to compressed columns leaves them.
+// ---------------------------------------------------------------------------------
+__global__ void k_elem_keys(int nel, int n, const int *__restrict__ rix, unsigned long long *__restrict__ key_ab, unsigned *__restrict__ val) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    const int *ids = rix + (size_t) e * n;
+    key_ab[e] = ((unsigned long long) (unsigned) ids[0] << 32) | (unsigned) ids[1];
+    val[e] = (unsigned) e;
+}
+
+// two elements of grade row with the same vertices: the reference would list both; left to it
+__global__ void k_dup_check(int nel, int n, const int *__restrict__ rix, const unsigned long long *__restrict__ key_sorted,
+                            const unsigned *__restrict__ val_sorted, unsigned *__restrict__ dup) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= nel || key_sorted[i] != key_sorted[i - 1]) return;
+    if (n == 2) { *dup = 1u; return; }
+    // triangles: the same leading pair is common (faces around an edge); compare the third id within the run
+    const int c = rix[(size_t) val_sorted[i] * 3 + 2];
+    for (int j = i - 1; j >= 0 && key_sorted[j] == key_sorted[i]; j--)
+        if (rix[(size_t) val_sorted[j] * 3 + 2] == c) { *dup = 1u; return; }
+}
+
+__global__ void k_lower(Combos cb, int ncol_el, const int *__restrict__ col_rix, int nrow_el, const int *__restrict__ row_rix,
+                        const unsigned long long *__restrict__ key_sorted, const unsigned *__restrict__ val_sorted,
+                        int *__restrict__ found, unsigned *__restrict__ count) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncol_el) return;
+    const int *ids = col_rix + (size_t) e * cb.nvper;
+    int got[6], n = 0;
+    for (int c = 0; c < cb.ncomb; c++) {
+        const unsigned a = (unsigned) ids[cb.idx[c][0]], b = (unsigned) ids[cb.idx[c][1]];
+        const unsigned long long key = ((unsigned long long) a << 32) | b;
+        long lo = 0, hi = nrow_el;
+        while (lo < hi) { long mid = (lo + hi) >> 1; if (key_sorted[mid] < key) lo = mid + 1; else hi = mid; }
+        int id = -1;
+        for (long i = lo; i < nrow_el && key_sorted[i] == key; i++) {
+            const int cand = (int) val_sorted[i];
+            if (cb.n == 2 || row_rix[(size_t) cand * 3 + 2] == ids[cb.idx[c][2]]) { id = cand; break; }
+        }
+        if (id < 0) continue;
+        int k = n++;                                   // insertion into the ascending list
+        while (k > 0 && got[k - 1] > id) { got[k] = got[k - 1]; k--; }
+        got[k] = id;
+    }
+    for (int k = 0; k < n; k++) found[(size_t) e * cb.ncomb + k] = got[k];
+    count[e] = (unsigned) n;
+}
+
+__global__ void k_lower_emit(int ncol_el, int ncomb, const int *__restrict__ found, const unsigned *__restrict__ count,
+                             const unsigned *__restrict__ cptr, int *__restrict__ out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncol_el) return;
+    for (unsigned k = 0; k < count[e]; k++) out[cptr[e] + k] = found[(size_t) e * ncomb + k];
+}
+
+extern "C" int mcu_mesh_lower(mcu_mesh *m, int row, int col, int *host_cptr, int *host_rix, int *nnz_out, int *nrows_out, int *ncols_out) {
+    if (!m || row < 1 || row > 2 || col <= row || col > 3 || !host_cptr || !host_rix || !nnz_out) { mcu_set_error("lower: bad arguments"); return MCU_ERR_ARGS; }
+    if (!m->conn[row].present || !m->conn[col].present) { mcu_set_error("lower: grades %d and %d must be present", row, col); return MCU_ERR_ELNOTFOUND; }
+    const McuConn &R = m->conn[row], &Cc = m->conn[col];
+    Combos cb;
+    cb.n = row + 1; cb.nvper = col + 1; cb.ncomb = 0;
+    if (cb.n == 2) { for (int a = 0; a <= col; a++) for (int b = a + 1; b <= col; b++) { cb.idx[cb.ncomb][0] = a; cb.idx[cb.ncomb][1] = b; cb.idx[cb.ncomb][2] = 0; cb.ncomb++; } }
+    else { for (int a = 0; a <= col; a++) for (int b = a + 1; b <= col; b++) for (int c = b + 1; c <= col; c++) { cb.idx[cb.ncomb][0] = a; cb.idx[cb.ncomb][1] = b; cb.idx[cb.ncomb][2] = c; cb.ncomb++; } }
+    cudaStream_t st = mcu_stream();
+    int rc = MCU_OK;
+    unsigned long long *key[2] = {nullptr, nullptr};
+    unsigned *val[2] = {nullptr, nullptr}, *count = nullptr, *cptr = nullptr, *dup = nullptr;
+    int *found = nullptr, *d_out = nullptr;
+    void *tmp = nullptr;
+    size_t t1 = 0, t2 = 0;
+    unsigned h_dup = 0, last_c = 0, last_p = 0;
+    const int nr = R.nel, nc = Cc.nel;
+    host_cptr[0] = 0;
+    *nnz_out = 0;
+    if (nrows_out) *nrows_out = 0;
+    if (ncols_out) *ncols_out = 0;
+    if (nc == 0) return MCU_OK;
+    CKC(cudaMalloc((void **) &key[0], 8 * (size_t) std::max(nr, 1))); CKC(cudaMalloc((void **) &key[1], 8 * (size_t) std::max(nr, 1)));
+    CKC(cudaMalloc((void **) &val[0], 4 * (size_t) std::max(nr, 1))); CKC(cudaMalloc((void **) &val[1], 4 * (size_t) std::max(nr, 1)));
+    CKC(cudaMalloc((void **) &count, 4 * (size_t) nc)); CKC(cudaMalloc((void **) &cptr, 4 * (size_t) nc));
+    CKC(cudaMalloc((void **) &found, sizeof(int) * (size_t) nc * cb.ncomb));
+    CKC(cudaMalloc((void **) &dup, 4));
+    CKC(cudaMemsetAsync(dup, 0, 4, st));
+    if (nr > 0) {
+        CKC(cub::DeviceRadixSort::SortPairs(nullptr, t1, key[0], key[1], val[0], val[1], nr, 0, 64, st));
+        CKC(cudaMalloc(&tmp, std::max<size_t>(t1, 16)));
+        k_elem_keys<<<(nr + 255) / 256, 256, 0, st>>>(nr, cb.n, R.d_rix, key[0], val[0]);
+        CKC(cub::DeviceRadixSort::SortPairs(tmp, t1, key[0], key[1], val[0], val[1], nr, 0, 64, st));
+        cudaFree(tmp); tmp = nullptr;
+        k_dup_check<<<(nr + 255) / 256, 256, 0, st>>>(nr, cb.n, R.d_rix, key[1], val[1], dup);
+    }
+    k_lower<<<(nc + 255) / 256, 256, 0, st>>>(cb, nc, Cc.d_rix, nr, R.d_rix, key[1], val[1], found, count);
+    CKC(cub::DeviceScan::ExclusiveSum(nullptr, t2, count, cptr, nc, st));
+    CKC(cudaMalloc(&tmp, std::max<size_t>(t2, 16)));
+    CKC(cub::DeviceScan::ExclusiveSum(tmp, t2, count, cptr, nc, st));
+    CKC(cudaMemcpyAsync(&h_dup, dup, 4, cudaMemcpyDeviceToHost, st));
+    CKC(cudaMemcpyAsync(&last_c, count + (nc - 1), 4, cudaMemcpyDeviceToHost, st));
+    CKC(cudaMemcpyAsync(&last_p, cptr + (nc - 1), 4, cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    g_mcu_launches += 4;
+    if (h_dup) { mcu_set_error("lower: two elements of grade %d have the same vertices", row); rc = MCU_ERR_UNSUPPORTED; goto done; }
+    {
+        const int nnz = (int) (last_c + last_p);
+        *nnz_out = nnz;
+        CKC(cudaMalloc((void **) &d_out, sizeof(int) * (size_t) std::max(nnz, 1)));
+        k_lower_emit<<<(nc + 255) / 256, 256, 0, st>>>(nc, cb.ncomb, found, count, cptr, d_out);
+        CKC(cudaMemcpyAsync(host_cptr, cptr, sizeof(int) * (size_t) nc, cudaMemcpyDeviceToHost, st));
+        CKC(cudaMemcpyAsync(host_rix, d_out, sizeof(int) * (size_t) nnz, cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+        host_cptr[nc] = nnz;
+        int mx = -1;
+        for (int i = 0; i < nnz; i++) mx = std::max(mx, host_rix[i]);
+        if (nrows_out) *nrows_out = mx + 1;            // the size a dictionary-of-keys matrix grows to (sparse.c:137-160):
+        int lastcol = nc;                              // largest row / column index with an entry, plus one
+        while (lastcol > 0 && host_cptr[lastcol] == host_cptr[lastcol - 1]) lastcol--;
+        if (ncols_out) *ncols_out = lastcol;
+        g_mcu_launches += 1;
+    }
+done:
+    for (int i = 0; i < 2; i++) { if (key[i]) cudaFree(key[i]); if (val[i]) cudaFree(val[i]); }
+    if (count) cudaFree(count);
+    if (cptr) cudaFree(cptr);
+    if (found) cudaFree(found);
+    if (dup) cudaFree(dup);
+    if (tmp) cudaFree(tmp);
+    if (d_out) cudaFree(d_out);
     return rc;
 }
 

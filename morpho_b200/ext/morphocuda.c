@@ -1155,6 +1155,63 @@ static value mc_Selection_constructor(vm *v, int nargs, value *args) {
     return orig_Selection_constructor(v, nargs, args);
 }
 
+/* conn(row, col), 1 <= row < col: the grade-lowering matrix (mesh_addlowermatrix, mesh.c:621-660) built on the device and
+ * installed where mesh_addconnectivityelement (mesh.c:663-685) would put it; everything that asks for it afterwards —
+ * Mesh.connectivitymatrix, selection_addgradelower (selection.c:129-155), the raise matrices (sparse_transpose of this
+ * one) — finds it there.  Returns false when nothing was built (already present, mesh too small, grades missing, ...). */
+static bool mc_ensure_lower(objectmesh *mesh, int row, int col) {
+    if (!mc_ready || row < 1 || col <= row || col > 3 || mesh_getconnectivityelement(mesh, (unsigned) row, (unsigned) col)) return false;
+    objectsparse *er = mesh_getconnectivityelement(mesh, 0, (unsigned) row), *ec = mesh_getconnectivityelement(mesh, 0, (unsigned) col);
+    if (!er || !ec || !sparse_checkformat(ec, SPARSE_CCS, true, false) || ec->ccs.ncols < mc_connect_min) return false;
+    mc_mirror *mr = mirror_get(mesh, (grade) row);
+    if (!mr || !mr->conn[row].ok) return false;
+    mr = mirror_get(mesh, (grade) col);
+    if (!mr || !mr->conn[col].ok) return false;
+    const int ncol = ec->ccs.ncols;
+    int ncomb = (col == 3 && row == 1) ? 6 : (col == 3 ? 4 : 3);
+    int *cptr = malloc(sizeof(int) * ((size_t) ncol + 1)), *rix = malloc(sizeof(int) * ((size_t) ncol * ncomb + 1));
+    int nnz = 0, nrows = 0, ncols = 0;
+    bool ok = cptr && rix && mcu_mesh_lower(mr->m, row, col, cptr, rix, &nnz, &nrows, &ncols) == MCU_OK;
+    objectsparse *new = ok ? object_newsparse(NULL, NULL) : NULL;
+    if (new && sparseccs_resize(&new->ccs, nrows, ncols, (unsigned) nnz, false)) {
+        memcpy(new->ccs.cptr, cptr, sizeof(int) * ((size_t) ncols + 1));
+        memcpy(new->ccs.rix, rix, sizeof(int) * (size_t) nnz);
+        mesh_setconnectivityelement(mesh, (unsigned) row, (unsigned) col, new);      /* mesh.c:655-656 */
+        mesh_link(mesh, (object *) new);
+        mesh_freezeconnectivity(mesh);
+        mc_stat_devops++;
+    } else {
+        if (!ok) mc_log("lowering matrix on the reference:", mcu_last_error());
+        if (new) object_free((object *) new);
+        ok = false;
+    }
+    free(cptr); free(rix);
+    return ok;
+}
+
+static builtinfunction orig_Mesh_connectivitymatrix = NULL;
+static value mc_Mesh_connectivitymatrix(vm *v, int nargs, value *args) {
+    if (mc_ready && nargs == 2 && MORPHO_ISINTEGER(MORPHO_GETARG(args, 0)) && MORPHO_ISINTEGER(MORPHO_GETARG(args, 1))) {
+        objectmesh *mesh = MORPHO_GETMESH(MORPHO_SELF(args));
+        int row = MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 0)), col = MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 1));
+        if (row >= 1 && col >= 1 && row <= 3 && col <= 3 && row != col)
+            mc_ensure_lower(mesh, row < col ? row : col, row < col ? col : row);     /* a raise matrix is the transpose of the lower one */
+    }
+    return orig_Mesh_connectivitymatrix(v, nargs, args);
+}
+
+/* Selection.addgrade(g) below the selection's highest grade walks conn(g, i) for every higher grade i
+ * (selection_addgradelower, selection.c:129-155) */
+static builtinfunction orig_Selection_addgrade = NULL;
+static value mc_Selection_addgrade(vm *v, int nargs, value *args) {
+    if (mc_ready && nargs > 0 && MORPHO_ISINTEGER(MORPHO_GETARG(args, 0))) {
+        objectselection *sel = MORPHO_GETSELECTION(MORPHO_SELF(args));
+        int g = MORPHO_GETINTEGERVALUE(MORPHO_GETARG(args, 0));
+        if (g >= 1 && sel->mesh) for (int i = g + 1; i <= 3 && i < (int) sel->ngrades + 1; i++) mc_ensure_lower(sel->mesh, g, i);
+    }
+    return orig_Selection_addgrade(v, nargs, args);
+}
+
 static int patch_function(const char *name, builtinfunction ours, builtinfunction *orig) {
     objectstring key = MORPHO_STATICSTRING((char *) name);
     value fv;
@@ -1258,6 +1315,8 @@ static void mc_core_initialize(void) {
         mc_boundaryoption = builtin_internsymbolascstring(SELECTION_BOUNDARYOPTION);
         npatched += patch_method("Mesh", MESH_ADDGRADE_METHOD, mc_Mesh_addgrade, &orig_Mesh_addgrade);
         npatched += patch_function(SELECTION_CLASSNAME, mc_Selection_constructor, &orig_Selection_constructor);
+        npatched += patch_method("Mesh", MESH_CONNECTIVITYMATRIX_METHOD, mc_Mesh_connectivitymatrix, &orig_Mesh_connectivitymatrix);
+        npatched += patch_method("Selection", SELECTION_ADDGRADEMETHOD, mc_Selection_addgrade, &orig_Selection_addgrade);
     }
 
     object probe;

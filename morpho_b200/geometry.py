@@ -109,6 +109,18 @@ class Mesh:
     def connectivity(self, g):
         return self._conn.get(g)
 
+    def lower(self, row, col):
+        """``(cptr, rix)`` of the grade-lowering connectivity matrix conn(row, col), 1 <= row < col
+        (``Mesh.connectivitymatrix(row, col)``; mesh_addlowermatrix, mesh.c:621-660): per element of grade ``col`` the ids,
+        ascending, of the elements of grade ``row`` it contains.  Built on the device (mcu_connect.cu)."""
+        ncol = self.count(col)
+        from math import comb
+        cptr = np.zeros(ncol + 1, dtype=np.int32)
+        rix = np.zeros(max(ncol * comb(col + 1, row + 1), 1), dtype=np.int32)
+        nnz, nrows, ncols = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(lib().mcu_mesh_lower(self._h, row, col, cptr.ctypes.data, rix.ctypes.data, C.byref(nnz), C.byref(nrows), C.byref(ncols)))
+        return cptr[: ncols.value + 1].copy(), rix[: nnz.value].copy(), nrows.value
+
     def addgrade(self, g):
         """Create grade ``g`` elements from the next higher grade present (mesh_addgrade, mesh.c:419-489)."""
         if g in self._conn:

@@ -165,7 +165,7 @@ def test_connectivity_is_built_on_the_device(tmp_path):
                    {"MORPHO_CUDA_VERBOSE": "1", "MORPHO_CUDA_CONNECT_MIN": "1000"})
     assert ref == new[:-1], (ref, new, err)
     stats = [int(float(v)) for v in NUM.findall(new[-1])]
-    assert stats[6] >= 6, (stats, err)              # device operations: 4 addgrade (AreaMesh already made the edges once) + 2 boundary selections
+    assert stats[6] >= 10, (stats, err)             # device operations: 4 addgrade + 2 boundary selections + 4 lowering matrices
     # below the threshold everything stays on the reference
     new2, _ = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext2.morpho", {"MORPHO_CUDA_CONNECT_MIN": "100000000"})
     assert ref == new2[:-1]

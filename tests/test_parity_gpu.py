@@ -300,6 +300,39 @@ def test_full_size_properties(mb, oracle):
             assert pv <= TOL_EXACT, (name, label, pv)
 
 
+def test_lowering_matrices_on_device_match_the_reference_bit_exactly(mb, reference):
+    """conn(row, col), row < col, built on the device (mcu_connect.cu: sort + binary search) against
+    mesh_addlowermatrix of the unmodified reference (mesh.c:621-660): the same compressed columns, entry for entry.
+    (1,2) on a closed surface, (1,2), (1,3) and (2,3) on tetrahedra, and a grade-1 that lacks some edges."""
+    from morpho_b200 import meshgen as mg
+    v, f = mg.icosphere(9)
+    v2, t = mg.tet_cube(4)
+    for vert, top, g_top, pairs in ((v, f, 2, ((1, 2),)), (v2, t, 3, ((2, 3), (1, 3), (1, 2)))):
+        kw = {"faces": top} if g_top == 2 else {"volumes": top}
+        m = mb.Mesh(vert, **kw)
+        rm = reference.mesh(vert, {g_top: top})
+        for g in range(g_top - 1, 0, -1):
+            m.addgrade(g)
+            rm.addgrade(g)
+        for row, col in pairs:
+            cptr, rix, nrows = m.lower(row, col)
+            want_cptr, want_rix = rm.conn(row, col, create=True)
+            np.testing.assert_array_equal(cptr, want_cptr)
+            np.testing.assert_array_equal(rix, want_rix)
+            assert nrows == m.count(row)
+        rm.free()
+    # edges given explicitly, every third one missing: columns of different length
+    edges = mg.edges_from_faces(f)[::3].copy()
+    m = mb.Mesh(v, edges=edges, faces=f)
+    rm = reference.mesh(v, {1: edges, 2: f})
+    cptr, rix, _ = m.lower(1, 2)
+    want_cptr, want_rix = rm.conn(1, 2, create=True)
+    np.testing.assert_array_equal(cptr, want_cptr)
+    np.testing.assert_array_equal(rix, want_rix)
+    assert len(set(np.diff(cptr).tolist())) > 1
+    rm.free()
+
+
 def test_addgrade_on_device_matches_the_reference_bit_exactly(mb, oracle, reference):
     """Mesh.addgrade built on the device (mcu_connect.cu: sort + scan) against mesh_addgrade of the unmodified
     reference (mesh.c:419-489): element ids in the order of first discovery, bit-exact.  Edges from triangles, edges
