@@ -315,3 +315,28 @@ def test_block_plan_reproduces_the_oracle_gradient(L, case):
     want = O.gradient(v, {g: c}, FunctionalSpec(name), sel)
     err = np.linalg.norm(got - want, axis=1).max() / np.linalg.norm(want, axis=1).max()
     assert err <= 1e-12, err
+
+
+def test_patch_plan_does_not_depend_on_the_number_of_threads(L):
+    """The planner cuts the top of the bisection tree level by level and builds the groups of patches on all host cores
+    (mcu_patch.cu); the pieces are concatenated in group order: headers, runs and tables are identical to the bit for
+    1, 3 and the default number of threads, and to the digest recorded from the single-threaded planner of round 1."""
+    import hashlib
+    from morpho_b200 import meshgen as mg
+    v, c = mg.icosphere(60)
+    v = np.ascontiguousarray(mg.perturb_radially(v))
+    c = np.ascontiguousarray(np.sort(c, axis=1).astype(np.int32))
+    digests = []
+    try:
+        for nt in (1, 3, 0):
+            assert L.mcu_set_option(b"plan_threads", nt) == 0
+            P = _plan(L, v, c, 0)
+            h = hashlib.sha256()
+            for a in (P["hdr"], P["runs"], P["tab"]):
+                h.update(np.ascontiguousarray(a).tobytes())
+            digests.append((h.hexdigest(), P["counts"]))
+    finally:
+        L.mcu_set_option(b"plan_threads", 0)
+    assert digests[0] == digests[1] == digests[2], digests
+    for pi, h in enumerate(P["hdr"]):                      # the patch index stored in every staged table is global
+        assert int(P["tab"][4 * int(h[H_TAB_OFF])]) == pi
