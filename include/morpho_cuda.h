@@ -226,7 +226,14 @@ enum {
      * element / the unit normal of a triangle in 3D; MCU_X_GRADQ a = 3 * (flattened field component) + k is the
      * derivative along x_k of the P1 interpolant of that component on a triangle (gradsq_evaluategradient) or a
      * tetrahedron in 3D (gradsq_evaluategradient3d) */
-    MCU_X_TANGENT = 27, MCU_X_NORMAL = 28, MCU_X_GRADQ = 29
+    MCU_X_TANGENT = 27, MCU_X_NORMAL = 28, MCU_X_GRADQ = 29,
+    /* control flow of a closure, branch free: comparisons give 1.0 / 0.0 with the VM's notion of equal floats
+     * (morpho_doubleeqtest, value.c:48-54: equal within DBL_EPSILON relative; vm.c:1095-1135), NOT of such a value, and
+     * SELECT pops (condition, then, else) — both sides of an `if` are evaluated, the condition picks one */
+    MCU_X_LT = 30, MCU_X_LE = 31, MCU_X_EQ = 32, MCU_X_NE = 33, MCU_X_NOT = 34, MCU_X_SELECT = 35,
+    /* common subexpressions: STORE copies the top of the stack into register a (0..31) and leaves it there, LOAD pushes
+     * register a; a register is stored before it is loaded */
+    MCU_X_STORE = 36, MCU_X_LOAD = 37
 };
 typedef struct mcu_expr_op { int op; int a; double c; } mcu_expr_op;
 int mcu_integral(mcu_mesh *m, int grade, int nops, const mcu_expr_op *prog, int nfields, mcu_field *const *fields,

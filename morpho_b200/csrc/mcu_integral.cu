@@ -25,6 +25,7 @@
 // barycentric coordinates of the root element, so a leaf contributes  value * (1/2 or 1/4)^depth  — the same number
 // the reference's nested averages produce, up to the association of the sums (1e-16).
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -95,9 +96,17 @@ struct MiView {
     unsigned *fail;                            // device word: set when an element needs more work items than a thread holds
 };
 
+// morpho_extendedcomparevalue on two floats (value.c:48-68): 0 when equal within DBL_EPSILON relative, +1 when b > a, else -1
+__device__ __forceinline__ int mi_cmp(double a, double b) {
+    if (a == b) return 0;
+    const double diff = fabs(a - b), absa = fabs(a), absb = fabs(b), absmax = absa > absb ? absa : absb;
+    if (diff == 0.0 || (absmax > DBL_MIN && diff / absmax <= DBL_EPSILON)) return 0;
+    return b > a ? 1 : -1;
+}
+
 // the postfix machine: ops c_prog[off .. off + len)
 __device__ __forceinline__ double mi_run(int off, int len, const double *x, const double *q) {
-    double st[MI_STACK];
+    double st[MI_STACK], rg[32];
     int sp = 0;
     for (int i = off; i < off + len; i++) {
         const mcu_expr_op op = c_prog[i];
@@ -129,6 +138,14 @@ __device__ __forceinline__ double mi_run(int off, int len, const double *x, cons
             case MCU_X_FLOOR: st[sp - 1] = floor(st[sp - 1]); break;
             case MCU_X_CEIL: st[sp - 1] = ceil(st[sp - 1]); break;
             case MCU_X_LOG10: st[sp - 1] = log10(st[sp - 1]); break;
+            case MCU_X_LT: sp--; st[sp - 1] = mi_cmp(st[sp - 1], st[sp]) > 0 ? 1.0 : 0.0; break;
+            case MCU_X_LE: sp--; st[sp - 1] = mi_cmp(st[sp - 1], st[sp]) >= 0 ? 1.0 : 0.0; break;
+            case MCU_X_EQ: sp--; st[sp - 1] = mi_cmp(st[sp - 1], st[sp]) == 0 ? 1.0 : 0.0; break;
+            case MCU_X_NE: sp--; st[sp - 1] = mi_cmp(st[sp - 1], st[sp]) != 0 ? 1.0 : 0.0; break;
+            case MCU_X_NOT: st[sp - 1] = st[sp - 1] != 0.0 ? 0.0 : 1.0; break;
+            case MCU_X_SELECT: sp -= 2; st[sp - 1] = st[sp - 1] != 0.0 ? st[sp] : st[sp + 1]; break;
+            case MCU_X_STORE: rg[op.a & 31] = st[sp - 1]; break;
+            case MCU_X_LOAD: st[sp++] = rg[op.a & 31]; break;
             default: break;
         }
     }
@@ -713,6 +730,7 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
     v.tn_slot = -1;
     std::vector<mcu_expr_op> rw(prog, prog + nops);
     int depth = 0;
+    unsigned stored = 0;
     for (int i = 0; i < nops; i++) {
         mcu_expr_op &op = rw[i];
         if (op.op == MCU_X_TANGENT || op.op == MCU_X_NORMAL) {
@@ -738,8 +756,11 @@ static int integral_setup(mcu_mesh *m, int grade, int nops, const mcu_expr_op *p
         if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
             if ((op.op == MCU_X_POS && (op.a < 0 || op.a > 2)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= v.nq))) { mcu_set_error("integrand operand out of range at op %d", i); return MCU_ERR_ARGS; }
             depth++;
-        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2) { if (depth < 2) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
-        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) { if (depth < 1) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2 || (op.op >= MCU_X_LT && op.op <= MCU_X_NE)) { if (depth < 2) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
+        else if ((op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) || op.op == MCU_X_NOT) { if (depth < 1) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        else if (op.op == MCU_X_SELECT) { if (depth < 3) { mcu_set_error("integrand stack underflow at op %d", i); return MCU_ERR_ARGS; } depth -= 2; }
+        else if (op.op == MCU_X_STORE) { if (depth < 1 || op.a < 0 || op.a > 31) { mcu_set_error("bad register store at op %d", i); return MCU_ERR_ARGS; } stored |= 1u << op.a; }
+        else if (op.op == MCU_X_LOAD) { if (op.a < 0 || op.a > 31 || !(stored & (1u << op.a))) { mcu_set_error("register loaded before it is stored at op %d", i); return MCU_ERR_ARGS; } depth++; }
         else { mcu_set_error("unknown integrand op %d", op.op); return MCU_ERR_ARGS; }
         if (depth > MI_STACK) { mcu_set_error("integrand stack too deep"); return MCU_ERR_UNSUPPORTED; }
     }
@@ -793,13 +814,17 @@ __global__ void __launch_bounds__(256) k_pw_grad(PwView v, double *out) {
 
 static int validate_program(const mcu_expr_op *prog, int nops, int dim, int nq, bool element_ops) {
     int depth = 0;
+    unsigned stored = 0;
     for (int i = 0; i < nops; i++) {
         const mcu_expr_op &op = prog[i];
         if (op.op == MCU_X_CONST || op.op == MCU_X_POS || op.op == MCU_X_FIELD) {
             if ((op.op == MCU_X_POS && (op.a < 0 || op.a >= dim)) || (op.op == MCU_X_FIELD && (op.a < 0 || op.a >= nq))) { mcu_set_error("operand out of range at op %d", i); return MCU_ERR_ARGS; }
             depth++;
-        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2) { if (depth < 2) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
-        else if (op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) { if (depth < 1) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        } else if ((op.op >= MCU_X_ADD && op.op <= MCU_X_DIV) || op.op == MCU_X_POW || op.op == MCU_X_ATAN2 || (op.op >= MCU_X_LT && op.op <= MCU_X_NE)) { if (depth < 2) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } depth--; }
+        else if ((op.op >= MCU_X_NEG && op.op <= MCU_X_LOG10) || op.op == MCU_X_NOT) { if (depth < 1) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } }
+        else if (op.op == MCU_X_SELECT) { if (depth < 3) { mcu_set_error("stack underflow at op %d", i); return MCU_ERR_ARGS; } depth -= 2; }
+        else if (op.op == MCU_X_STORE) { if (depth < 1 || op.a < 0 || op.a > 31) { mcu_set_error("bad register store at op %d", i); return MCU_ERR_ARGS; } stored |= 1u << op.a; }
+        else if (op.op == MCU_X_LOAD) { if (op.a < 0 || op.a > 31 || !(stored & (1u << op.a))) { mcu_set_error("register loaded before it is stored at op %d", i); return MCU_ERR_ARGS; } depth++; }
         else if (element_ops && op.op >= MCU_X_TANGENT && op.op <= MCU_X_GRADQ) depth++;
         else { mcu_set_error("op %d not allowed here", op.op); return MCU_ERR_ARGS; }
         if (depth > MI_STACK) { mcu_set_error("expression stack too deep"); return MCU_ERR_UNSUPPORTED; }

@@ -8,7 +8,11 @@
  * their semantics, incl. Int/Float promotion), calls of the real math builtins (functiondefs.c:659-695), calls of other
  * Morpho functions (inlined), element-wise vector arithmetic on the position / matrix-valued quantities, `norm`,
  * `inner`, `sum`, `trace`, `count`, and the element helpers tangent(), normal(), grad(q) (constants of the element).
- * Anything else (branches, loops, lists, printing, writes to globals ...) makes the translation fail, and the caller runs the reference builtin instead.
+ * Control flow: comparisons (EQ NEQ LT LE with the VM's tolerance for equal floats), NOT and the branches B BIF BIFF.  A
+ * branch on a value known at translation time is simply followed (loops with constant bounds unroll); a branch on a value
+ * that depends on the position or a field FORKS the interpretation: both continuations run to their RETURN and the result
+ * is SELECT(condition, taken, not taken) — the device evaluates both sides, branch free.
+ * Anything else (for-in over collections, lists, printing, writes to globals ...) makes the translation fail, and the caller runs the reference builtin instead.
  * Globals and upvalues are read at translation time; the translation is redone at every evaluation.
  */
 #ifndef MC_TRANSLATE_H
@@ -26,8 +30,8 @@
 #define MT_MAXCOMP 9
 #define MT_MAXDEPTH 6
 
-typedef struct { int op, a, b, isint; double c; } mt_node;        /* op: MCU_X_*;  CONST: c (isint: a Morpho Int) */
-typedef enum { MT_NONE, MT_NUM, MT_VEC, MT_OBJ, MT_GRADLIST } mt_kind;
+typedef struct { int op, a, b, d, isint; double c; } mt_node;     /* op: MCU_X_*;  CONST: c (isint: a Morpho Int); SELECT: a ? b : d */
+typedef enum { MT_NONE, MT_NUM, MT_VEC, MT_OBJ, MT_GRADLIST, MT_BOOL } mt_kind;     /* MT_BOOL: node[0] evaluates to 1.0 / 0.0 */
 /* field >= 0: the symbol still IS the interpolated value of that Field argument (what grad() looks up, functional.c:4644-4652);
  * qbase: its first flattened component.  MT_GRADLIST: grad(q) of a matrix-valued q, a List of dim matrices. */
 typedef struct { mt_kind kind; int nrows, ncols; int node[MT_MAXCOMP]; value obj; int field, qbase; } mt_sym;
@@ -35,6 +39,7 @@ typedef struct {
     vm *v;
     mt_node nodes[MT_MAXNODES];
     int nnodes, depth, dim;
+    int steps, forks;                                    /* budget of interpreted instructions / nested forks, shared by all paths */
     int nfields, fqbase[16], frows[16], fcols[16];      /* the Field arguments: first flattened component and shape */
     value fieldobj[16];                                  /* the Field objects themselves, for grad(Field) (functional.c:4644-4646) */
     const char *why;
@@ -43,9 +48,18 @@ typedef struct {
 static bool mt_fail(mt_ctx *c, const char *why) { if (!c->why) c->why = why; return false; }
 
 static int mt_new(mt_ctx *c, int op, int a, int b, double k, int isint) {
+    /* structural sharing: the same operation on the same operands is the same node, so that the two continuations of a
+     * forked branch (and `var a = ...; a*a`) share what they have in common and mt_emit computes it once.  SELECT nodes
+     * get their third operand after creation and are never shared here. */
+    if (op != MCU_X_SELECT)
+        for (int i = c->nnodes - 1; i >= 0 && i >= c->nnodes - 512; i--) {
+            const mt_node *n = &c->nodes[i];
+            if (n->op == op && n->a == a && n->b == b && n->isint == isint && n->op != MCU_X_SELECT &&
+                (n->c == k && signbit(n->c) == signbit(k))) return i;
+        }
     if (c->nnodes == MT_MAXNODES) { mt_fail(c, "expression too large"); return -1; }
     mt_node *n = &c->nodes[c->nnodes];
-    n->op = op; n->a = a; n->b = b; n->c = k; n->isint = isint;
+    n->op = op; n->a = a; n->b = b; n->d = 0; n->c = k; n->isint = isint;
     return c->nnodes++;
 }
 static int mt_constf(mt_ctx *c, double x) { return mt_new(c, MCU_X_CONST, 0, 0, x, 0); }
@@ -97,10 +111,46 @@ static int mt_unary(mt_ctx *c, int op, int x) {
     return mt_new(c, op, x, 0, 0.0, 0);      /* operand in a */
 }
 
+/* morpho_extendedcomparevalue on numbers (value.c:48-120): 0 equal (floats: within DBL_EPSILON relative), +1 if b > a, else -1 */
+static int mt_cmpconst(const mt_node *a, const mt_node *b) {
+    if (a->isint && b->isint) return a->a == b->a ? 0 : (b->a > a->a ? 1 : -1);
+    const double x = a->c, y = b->c;
+    if (x == y) return 0;
+    const double diff = fabs(x - y), ax = fabs(x), ay = fabs(y), amax = ax > ay ? ax : ay;
+    if (diff == 0.0 || (amax > DBL_MIN && diff / amax <= DBL_EPSILON)) return 0;
+    return y > x ? 1 : -1;
+}
+static mt_sym mt_bool(int node) { mt_sym s; memset(&s, 0, sizeof(s)); s.kind = node >= 0 ? MT_BOOL : MT_NONE; s.node[0] = node; s.obj = MORPHO_NIL; s.field = -1; return s; }
+/* EQ NEQ LT LE on two numbers (vm.c:1095-1135) */
+static mt_sym mt_compare(mt_ctx *c, int op, const mt_sym *l, const mt_sym *r) {
+    if (l->kind != MT_NUM || r->kind != MT_NUM) { mt_fail(c, "comparison of something that is not a number"); return mt_none(); }
+    const int a = l->node[0], b = r->node[0];
+    if (mt_isconst(c, a) && mt_isconst(c, b)) {
+        const int k = mt_cmpconst(&c->nodes[a], &c->nodes[b]);
+        const bool t = op == MCU_X_LT ? k > 0 : (op == MCU_X_LE ? k >= 0 : (op == MCU_X_EQ ? k == 0 : k != 0));
+        return mt_bool(mt_constf(c, t ? 1.0 : 0.0));
+    }
+    return mt_bool(mt_new(c, op, a, b, 0.0, 0));
+}
+/* the truth value a branch sees (morpho_isfalse, value.c:136-138): nil and false are false, everything else is true.
+ * Returns 1 / 0 when known at translation time, -1 when it depends on the point (then *node is the 1.0 / 0.0 expression) */
+static int mt_truth(mt_ctx *c, const mt_sym *s, int *node) {
+    if (s->kind == MT_BOOL) {
+        if (mt_isconst(c, s->node[0])) return c->nodes[s->node[0]].c != 0.0 ? 1 : 0;
+        *node = s->node[0];
+        return -1;
+    }
+    if (s->kind == MT_NONE) return 0;                                    /* nil */
+    if (s->kind == MT_OBJ && MORPHO_ISBOOL(s->obj)) return MORPHO_GETBOOLVALUE(s->obj) ? 1 : 0;
+    if (s->kind == MT_OBJ && MORPHO_ISNIL(s->obj)) return 0;
+    return 1;
+}
+
 /* a runtime value (constant table, global, upvalue, argument) as a symbol */
 static mt_sym mt_fromvalue(mt_ctx *c, value val) {
     if (MORPHO_ISFLOAT(val)) return mt_num(mt_constf(c, MORPHO_GETFLOATVALUE(val)));
     if (MORPHO_ISINTEGER(val)) return mt_num(mt_consti(c, MORPHO_GETINTEGERVALUE(val)));
+    if (MORPHO_ISBOOL(val)) return mt_bool(mt_constf(c, MORPHO_GETBOOLVALUE(val) ? 1.0 : 0.0));
     mt_sym s = mt_none();
     if (MORPHO_ISMATRIX(val)) {                /* a constant Matrix captured by the closure */
         objectmatrix *m = MORPHO_GETMATRIX(val);
@@ -150,7 +200,8 @@ static const char *mt_builtinname(value fn) {
 static bool mt_sameshape(const mt_sym *a, const mt_sym *b) { return a->kind == MT_VEC && b->kind == MT_VEC && a->nrows == b->nrows && a->ncols == b->ncols; }
 
 /* reg[a] = reg[b] op reg[c] for scalars and (element-wise) vectors, as Matrix_add/sub/mul/div do */
-static bool mt_arith(mt_ctx *c, int op, const mt_sym *l, const mt_sym *r, mt_sym *out) {
+static bool mt_arith(mt_ctx *c, int op, const mt_sym *lp, const mt_sym *rp, mt_sym *out) {
+    const mt_sym lv = *lp, rv = *rp, *l = &lv, *r = &rv;          /* `i = i + 1` writes the register it reads */
     *out = mt_none();
     if (l->kind == MT_NUM && r->kind == MT_NUM) { *out = mt_num(mt_binary(c, op, l->node[0], r->node[0])); return out->kind == MT_NUM || mt_fail(c, "arithmetic"); }
     const int n = (l->kind == MT_VEC ? l : r)->nrows * (l->kind == MT_VEC ? l : r)->ncols;
@@ -290,6 +341,47 @@ static bool mt_call(mt_ctx *c, const mt_sym *callee, const mt_sym *args, int nar
     return mt_fail(c, "call of a builtin the device does not have");
 }
 
+#define MT_MAXSTEPS 20000
+#define MT_MAXFORKS 24
+#define MT_NREG (MORPHO_MAXREGISTERS + 8)            /* INVOKE touches reg[a + 2] */
+
+static int mt_select(mt_ctx *c, int cond, int a, int b) {
+    if (cond < 0 || a < 0 || b < 0) return -1;
+    if (a == b) return a;
+    int n = mt_new(c, MCU_X_SELECT, cond, a, 0.0, 0);
+    if (n >= 0) c->nodes[n].d = b;
+    return n;
+}
+
+static bool mt_exec(mt_ctx *c, objectfunction *func, objectclosure *closure, mt_sym *reg, const instruction *pc, mt_sym *ret);
+
+/* a branch whose condition depends on the point: both continuations to their RETURN, merged with SELECT */
+static bool mt_fork(mt_ctx *c, objectfunction *func, objectclosure *closure, const mt_sym *reg, int cond,
+                    const instruction *pc_true, const instruction *pc_false, mt_sym *ret) {
+    if (++c->forks > MT_MAXFORKS) return mt_fail(c, "too many data-dependent branches");
+    mt_sym *copy = (mt_sym *) malloc(sizeof(mt_sym) * MT_NREG);
+    if (!copy) return mt_fail(c, "allocation");
+    mt_sym r1, r2;
+    memcpy(copy, reg, sizeof(mt_sym) * MT_NREG);
+    bool ok = mt_exec(c, func, closure, copy, pc_true, &r1);
+    if (ok) {
+        memcpy(copy, reg, sizeof(mt_sym) * MT_NREG);
+        ok = mt_exec(c, func, closure, copy, pc_false, &r2);
+    }
+    free(copy);
+    if (!ok) return false;
+    if (r1.kind != r2.kind || (r1.kind != MT_NUM && r1.kind != MT_VEC && r1.kind != MT_BOOL) ||
+        (r1.kind == MT_VEC && (r1.nrows != r2.nrows || r1.ncols != r2.ncols))) return mt_fail(c, "the branches of an if return different kinds of value");
+    *ret = r1;
+    ret->field = -1;
+    const int ncomp = r1.kind == MT_VEC ? r1.nrows * r1.ncols : 1;
+    for (int i = 0; i < ncomp; i++) {
+        ret->node[i] = mt_select(c, cond, r1.node[i], r2.node[i]);
+        if (ret->node[i] < 0) return false;
+    }
+    return true;
+}
+
 static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym *ret) {
     objectclosure *closure = NULL;
     objectfunction *func;
@@ -299,15 +391,23 @@ static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym
     if (func->nargs != nargs || func->varg >= 0 || func->opt.count > 0 || func->nopt > 0) return mt_fail(c, "argument count / optional arguments");
     if (++c->depth > MT_MAXDEPTH) return mt_fail(c, "call depth");
     if (!c->v->instructions) return mt_fail(c, "no program");
-    mt_sym *reg = (mt_sym *) malloc(sizeof(mt_sym) * (MORPHO_MAXREGISTERS + 8));      /* INVOKE touches reg[a + 2] */
+    mt_sym *reg = (mt_sym *) malloc(sizeof(mt_sym) * MT_NREG);
     if (!reg) return mt_fail(c, "allocation");
-    for (int i = 0; i < MORPHO_MAXREGISTERS + 8; i++) reg[i] = mt_none();
+    for (int i = 0; i < MT_NREG; i++) reg[i] = mt_none();
     reg[0] = mt_none(); reg[0].kind = MT_OBJ; reg[0].obj = fn;
     for (int i = 0; i < nargs; i++) reg[i + 1] = args[i];
     for (int i = nargs + 1; i < func->nregs && i <= MORPHO_MAXREGISTERS; i++) reg[i] = mt_num(mt_consti(c, 0));   /* vm.c:733 */
+    bool ok = mt_exec(c, func, closure, reg, c->v->instructions + func->entry, ret);
+    free(reg);
+    c->depth--;
+    return ok && !c->why;
+}
+
+/* interpret from pc to the RETURN of this function; reg is this path's private register file */
+static bool mt_exec(mt_ctx *c, objectfunction *func, objectclosure *closure, mt_sym *reg, const instruction *pc, mt_sym *ret) {
     bool ok = false, done = false;
-    const instruction *pc = c->v->instructions + func->entry;
-    for (int steps = 0; !done && steps < 4096; steps++, pc++) {
+    for (; !done; pc++) {
+        if (++c->steps > MT_MAXSTEPS) { mt_fail(c, "too many instructions (a loop that does not end at translation time?)"); break; }
         const instruction bc = *pc;
         const int a = DECODE_A(bc), b = DECODE_B(bc), cc = DECODE_C(bc);
         switch (DECODE_OP(bc)) {
@@ -369,52 +469,111 @@ static bool mt_interp(mt_ctx *c, value fn, const mt_sym *args, int nargs, mt_sym
                 reg[a + 1] = out;
                 break;
             }
+            case OP_EQ: reg[a] = mt_compare(c, MCU_X_EQ, &reg[b], &reg[cc]); if (reg[a].kind != MT_BOOL) done = true; break;
+            case OP_NEQ: reg[a] = mt_compare(c, MCU_X_NE, &reg[b], &reg[cc]); if (reg[a].kind != MT_BOOL) done = true; break;
+            case OP_LT: reg[a] = mt_compare(c, MCU_X_LT, &reg[b], &reg[cc]); if (reg[a].kind != MT_BOOL) done = true; break;
+            case OP_LE: reg[a] = mt_compare(c, MCU_X_LE, &reg[b], &reg[cc]); if (reg[a].kind != MT_BOOL) done = true; break;
+            case OP_NOT: {                          /* vm.c:1084-1093: !bool, else "is nil" */
+                int node = -1;
+                if (reg[b].kind == MT_BOOL) {
+                    const int t = mt_truth(c, &reg[b], &node);
+                    reg[a] = mt_bool(t >= 0 ? mt_constf(c, t ? 0.0 : 1.0) : mt_new(c, MCU_X_NOT, node, 0, 0.0, 0));
+                } else reg[a] = mt_bool(mt_constf(c, reg[b].kind == MT_NONE ? 1.0 : 0.0));
+                if (reg[a].kind != MT_BOOL) done = true;
+                break;
+            }
+            case OP_B: pc += DECODE_sBx(bc); break;
+            case OP_BIF:
+            case OP_BIFF: {
+                int node = -1;
+                const int t = mt_truth(c, &reg[a], &node);
+                const bool jump_if = DECODE_OP(bc) == OP_BIF;
+                if (t >= 0) { if ((t == 1) == jump_if) pc += DECODE_sBx(bc); break; }
+                /* the condition depends on the point: follow both ways (the loop's pc++ is part of a continuation's start) */
+                const instruction *jump = pc + DECODE_sBx(bc) + 1, *fall = pc + 1;
+                ok = mt_fork(c, func, closure, reg, node, jump_if ? jump : fall, jump_if ? fall : jump, ret);
+                done = true;
+                break;
+            }
             case OP_RETURN:
-                if (a > 0) { *ret = reg[b]; ok = ret->kind == MT_NUM || ret->kind == MT_VEC; if (!ok) mt_fail(c, "function returns something that is not a number"); }
+                if (a > 0) { *ret = reg[b]; ok = ret->kind == MT_NUM || ret->kind == MT_VEC || ret->kind == MT_BOOL; if (!ok) mt_fail(c, "function returns something that is not a number"); }
                 else mt_fail(c, "function returns nil");
                 done = true;
                 break;
             default:
-                mt_fail(c, "control flow or an instruction the translator does not handle");
+                mt_fail(c, "an instruction the translator does not handle");
                 done = true;
         }
     }
-    free(reg);
-    c->depth--;
     return ok && !c->why;
 }
 
-/* postfix emission; shared subexpressions are re-emitted (the program has no registers) */
-static bool mt_emit(mt_ctx *c, int node, mcu_expr_op *prog, int *n, int cap) {
-    /* explicit stack: expressions from long sums are deep on the left */
+/* Postfix emission.  A node that is used more than once (and is not a leaf) is computed once: MCU_X_STORE r behind its
+ * first evaluation keeps the value in register r of the device's small register file, MCU_X_LOAD r fetches it later.
+ * The device evaluates both sides of every SELECT, so "first evaluation" is simply first in program order. */
+#define MT_NREGS 32
+static bool mt_emit(mt_ctx *c, int root, mcu_expr_op *prog, int *n, int cap) {
     typedef struct { int node, stage; } frame;
     frame *st = (frame *) malloc(sizeof(frame) * (MT_MAXNODES + 8));
-    if (!st) return mt_fail(c, "allocation");
+    short *uses = (short *) calloc((size_t) c->nnodes + 1, sizeof(short)), *regof = (short *) malloc(sizeof(short) * ((size_t) c->nnodes + 1));
+    if (!st || !uses || !regof) { free(st); free(uses); free(regof); return mt_fail(c, "allocation"); }
+    for (int i = 0; i < c->nnodes; i++) regof[i] = -1;
+#define MT_LEAF(nd) ((nd)->op == MCU_X_CONST || (nd)->op == MCU_X_POS || (nd)->op == MCU_X_FIELD || (nd)->op == MCU_X_TANGENT || \
+                     (nd)->op == MCU_X_NORMAL || (nd)->op == MCU_X_GRADQ)
+#define MT_BINARY(nd) (((nd)->op >= MCU_X_ADD && (nd)->op <= MCU_X_DIV) || (nd)->op == MCU_X_POW || (nd)->op == MCU_X_ATAN2 || \
+                       ((nd)->op >= MCU_X_LT && (nd)->op <= MCU_X_NE) || (nd)->op == MCU_X_SELECT)
+    /* pass 1: how often is every node reached from the root (a node's operands are counted once, on its first visit) */
     int sp = 0;
+    st[sp++].node = root;
+    while (sp > 0) {
+        const int id = st[--sp].node;
+        if (uses[id]++ > 0) continue;
+        const mt_node *nd = &c->nodes[id];
+        if (MT_LEAF(nd)) continue;
+        if (sp + 3 >= MT_MAXNODES) { free(st); free(uses); free(regof); return mt_fail(c, "expression too deep"); }
+        st[sp++].node = nd->op == MCU_X_POWI ? nd->b : nd->a;
+        if (MT_BINARY(nd)) st[sp++].node = nd->b;
+        if (nd->op == MCU_X_SELECT) st[sp++].node = nd->d;
+    }
+    /* pass 2: emit */
+    int nregs = 0;
     bool ok = true;
-    st[sp].node = node; st[sp++].stage = 0;
+    sp = 0;
+    st[sp].node = root; st[sp++].stage = 0;
     while (sp > 0 && ok) {
         frame *f = &st[sp - 1];
         const mt_node *nd = &c->nodes[f->node];
-        const bool leaf = nd->op == MCU_X_CONST || nd->op == MCU_X_POS || nd->op == MCU_X_FIELD || nd->op == MCU_X_TANGENT ||
-                          nd->op == MCU_X_NORMAL || nd->op == MCU_X_GRADQ;
-        const bool binary = (nd->op >= MCU_X_ADD && nd->op <= MCU_X_DIV) || nd->op == MCU_X_POW || nd->op == MCU_X_ATAN2;
+        const bool leaf = MT_LEAF(nd), binary = MT_BINARY(nd), ternary = nd->op == MCU_X_SELECT;
         if (sp >= MT_MAXNODES) { ok = mt_fail(c, "expression too deep"); break; }
         if (!leaf && f->stage == 0) {
+            if (regof[f->node] >= 0) {                 /* computed before: fetch it */
+                if (*n >= cap) { ok = mt_fail(c, "integrand program too long"); break; }
+                prog[*n].op = MCU_X_LOAD; prog[*n].a = regof[f->node]; prog[*n].c = 0.0; (*n)++;
+                sp--;
+                continue;
+            }
             f->stage = 1;
             /* POWI keeps its operand in b (a is the exponent); unary ops keep it in a */
             st[sp].node = nd->op == MCU_X_POWI ? nd->b : nd->a; st[sp++].stage = 0;
             continue;
         }
         if (binary && f->stage == 1) { f->stage = 2; st[sp].node = nd->b; st[sp++].stage = 0; continue; }
+        if (ternary && f->stage == 2) { f->stage = 3; st[sp].node = nd->d; st[sp++].stage = 0; continue; }
         if (*n >= cap) { ok = mt_fail(c, "integrand program too long"); break; }
         prog[*n].op = nd->op;
         prog[*n].a = ((leaf && nd->op != MCU_X_CONST) || nd->op == MCU_X_POWI) ? nd->a : 0;
         prog[*n].c = nd->op == MCU_X_CONST ? nd->c : 0.0;
         (*n)++;
+        if (!leaf && uses[f->node] > 1 && nregs < MT_NREGS) {
+            if (*n >= cap) { ok = mt_fail(c, "integrand program too long"); break; }
+            regof[f->node] = (short) nregs;
+            prog[*n].op = MCU_X_STORE; prog[*n].a = nregs++; prog[*n].c = 0.0; (*n)++;
+        }
         sp--;
     }
-    free(st);
+#undef MT_LEAF
+#undef MT_BINARY
+    free(st); free(uses); free(regof);
     return ok;
 }
 
@@ -472,6 +631,7 @@ static bool mc_translate_pointfn(vm *v, value fn, int dim, mcu_expr_op *prog, in
     mt_sym args[3], ret;
     for (int i = 0; i < dim && i < 3; i++) args[i] = mt_num(mt_new(c, MCU_X_POS, i, 0, 0.0, 0));
     bool ok = dim >= 1 && dim <= 3 && mt_interp(c, fn, args, dim, &ret);
+    if (ok && ret.kind != MT_NUM && ret.kind != MT_VEC) ok = mt_fail(c, "function does not return a number or a Matrix");
     *nprog = 0;
     int total = 0;
     if (ok) {

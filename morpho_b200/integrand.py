@@ -13,13 +13,13 @@ import numpy as np
 OPS = {"const": 0, "pos": 1, "field": 2, "add": 3, "sub": 4, "mul": 5, "div": 6, "neg": 7, "powi": 8, "sqrt": 9,
        "sin": 10, "cos": 11, "exp": 12, "log": 13, "abs": 14, "pow": 15, "tan": 16, "asin": 17, "acos": 18,
        "atan": 19, "atan2": 20, "sinh": 21, "cosh": 22, "tanh": 23, "floor": 24, "ceil": 25, "log10": 26,
-       "tangent": 27, "normal": 28, "gradq": 29}
-BINARY = ("add", "sub", "mul", "div", "pow", "atan2")
+       "tangent": 27, "normal": 28, "gradq": 29, "lt": 30, "le": 31, "eq": 32, "ne": 33, "not": 34, "select": 35, "store": 36, "load": 37}
+BINARY = ("add", "sub", "mul", "div", "pow", "atan2", "lt", "le", "eq", "ne")
 
 OP_DTYPE = np.dtype([("op", "<i4"), ("a", "<i4"), ("c", "<f8")])
 
 __all__ = ["Expr", "trace", "sqrt", "sin", "cos", "exp", "log", "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh",
-           "tanh", "floor", "ceil", "log10", "tangent", "normal", "grad", "trace_point", "OPS", "OP_DTYPE"]
+           "tanh", "floor", "ceil", "log10", "tangent", "normal", "grad", "trace_point", "OPS", "OP_DTYPE", "where", "lt", "le"]
 
 
 class Expr:
@@ -78,6 +78,21 @@ floor, ceil, log10 = _fn("floor"), _fn("ceil"), _fn("log10")
 
 def atan2(y, x):
     return Expr.lift(y)._bin(x, "atan2")
+
+
+def lt(a, b):
+    """1.0 where a < b, else 0.0 — with the VM's tolerance for equal floats (include/morpho_cuda.h, MCU_X_LT)."""
+    return Expr.lift(a)._bin(b, "lt")
+
+
+def le(a, b):
+    return Expr.lift(a)._bin(b, "le")
+
+
+def where(cond, a, b):
+    """``a`` where ``cond`` is non-zero, else ``b`` (MCU_X_SELECT): what an ``if`` in a Morpho closure translates to."""
+    c, x, y = Expr.lift(cond), Expr.lift(a), Expr.lift(b)
+    return Expr(c.prog + x.prog + y.prog + [(OPS["select"], 0, 0.0)])
 
 
 class _Q(Expr):

@@ -83,8 +83,28 @@ def _run_program(prog, x, q):
           24: lambda a: float(math.floor(a)), 25: lambda a: float(math.ceil(a)), 26: math.log10}
     bi = {3: lambda a, b: a + b, 4: lambda a, b: a - b, 5: lambda a, b: a * b, 6: lambda a, b: a / b,
           15: math.pow, 20: math.atan2}
-    st = []
+    def cmp(a, b):                       # morpho_extendedcomparevalue on floats (value.c:48-68)
+        if a == b:
+            return 0
+        diff, amax = abs(a - b), max(abs(a), abs(b))
+        if diff == 0.0 or (amax > 2.2250738585072014e-308 and diff / amax <= 2.220446049250313e-16):
+            return 0
+        return 1 if b > a else -1
+    bi.update({30: lambda a, b: float(cmp(a, b) > 0), 31: lambda a, b: float(cmp(a, b) >= 0),
+               32: lambda a, b: float(cmp(a, b) == 0), 33: lambda a, b: float(cmp(a, b) != 0)})
+    un[34] = lambda a: 0.0 if a != 0.0 else 1.0
+    st, rg = [], {}
     for op, a, c in prog:
+        if op == 36:                     # STORE: keep the top of the stack in register a
+            rg[a] = st[-1]
+            continue
+        if op == 37:                     # LOAD
+            st.append(rg[a])
+            continue
+        if op == 35:                     # SELECT: condition, then, else
+            e, t, cnd = st.pop(), st.pop(), st.pop()
+            st.append(t if cnd != 0.0 else e)
+            continue
         if op == 0:
             st.append(c)
         elif op == 1:
@@ -112,7 +132,8 @@ def test_closure_translator_reproduces_the_vm(tmp_path):
     tm = [[1.0, -0.3, 0.2, 0.7], [0.4, 0.9, -1.1, 0.05]]           # column-major 2x2
     quantities = {"f0": lambda i: [], "f1": lambda i: [p[i]] + qv[i], "f2": lambda i: qv[i], "f3": lambda i: qv[i],
                   "f4": lambda i: [], "f5": lambda i: tm[i], "f6": lambda i: [], "f7": lambda i: [], "f8": lambda i: [p[i]],
-                  "f9": lambda i: []}
+                  "f9": lambda i: [], "c0": lambda i: [], "c1": lambda i: [], "c2": lambda i: [], "c3": lambda i: [p[i]],
+                  "c4": lambda i: qv[i], "c5": lambda i: []}
     progs, vals, fails = {}, {}, {}
     for line in out:
         w = line.split()
@@ -144,7 +165,7 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
     stats = [int(v) for v in NUM.findall(new[-1])]
     evals, fallbacks, translated = stats[0], stats[3], stats[5]
-    assert translated == 73 and evals >= 73 and fallbacks == 1, (stats, err)    # 30 values + 22 gradients + 7 potentials + 14 with a method dictionary; 1 untranslatable
+    assert translated == 74 and evals >= 74 and fallbacks == 0, (stats, err)    # 30 values + 22 gradients + 8 potentials + 14 with a method dictionary
     cut = ref.index("-- gradients")
     compare(ref[:cut], new[:cut], 1e-12)
     cut2 = ref.index("-- potentials")
@@ -152,6 +173,23 @@ def test_integral_closures_run_on_the_gpu(tmp_path):
     cut3 = ref.index("-- methods")
     compare(ref[cut2:cut3], new[cut2:cut3], 1e-9) # potentials: exact gradient function 1e-12-ish, FD variant 1e-10
     compare(ref[cut3:], new[cut3:-1], 1e-12)      # the rule-table integrator (method dictionaries)
+
+
+@pytest.mark.gpu
+def test_closures_with_control_flow_run_on_the_gpu(tmp_path):
+    """Integrands and potentials that branch on the point (if / else if / &&, || / early returns, helper functions with
+    branches, loops with constant bounds): translated into branch-free programs (SELECT, shared subexpressions in
+    registers) and evaluated on the device.  Values at 1e-10 (the integrands are discontinuous: the adaptive quadrature
+    refines to its depth limit along the jumps), finite-difference gradients at 1e-7."""
+    src = script("control_flow.morpho")
+    ref, _ = run(src, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + src + "\nprint cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    stats = [int(float(v)) for v in NUM.findall(new[-1])]
+    evals, fallbacks, translated = stats[0], stats[3], stats[5]
+    assert translated == 20 and fallbacks == 0, (stats, err)       # 6 x (total, integrand, gradient) + potential total / gradient
+    cut = ref.index("-- gradients")
+    compare(ref[:cut], new[:cut], 1e-10)
+    compare(ref[cut:], new[cut:-1], 1e-7)
 
 
 @pytest.mark.gpu
@@ -291,7 +329,7 @@ def test_pairwise_potential_behind_the_script_api(tmp_path, resident_min):
     assert "ready:" in err and "PairwisePotential patched" in err, err
     stats = [float(x) for x in NUM.findall(new[-1])]
     evals, fallbacks = stats[0], stats[3]
-    assert evals == 7 * 3 and fallbacks == 3, (stats, err)
+    assert evals == 8 * 3 and fallbacks == 0, (stats, err)          # incl. "hertz", whose closures branch on r
     compare(ref, new[:-1], 1e-11)
 
 
