@@ -69,9 +69,11 @@ cp -f "$REF"/modules/*.morpho "$OUT/pkg/share/modules/"
 # them through the extension as well (tests/test_extension.py).  Build output only: oracle/_ref is never committed.
 rm -rf "$OUT/reftests"; mkdir -p "$OUT/reftests"
 for d in functionals selection field mesh; do cp -r "$REF/test/$d" "$OUT/reftests/$d"; done
-# the shipped examples named by BASELINE.json's configs (catenoid, thomson, tactoid), run AS SHIPPED by the tests
+# the shipped examples that exercise the hot path (BASELINE.json configs: catenoid, thomson, tactoid; and qtensor, cholesteric,
+# electrostatics, cube), run AS SHIPPED by the tests
 rm -rf "$OUT/examples"; mkdir -p "$OUT/examples"
-for d in catenoid thomson tactoid; do cp -r "$REF/examples/$d" "$OUT/examples/$d"; done
+for d in catenoid thomson tactoid qtensor cholesteric electrostatics cube; do cp -r "$REF/examples/$d" "$OUT/examples/$d"; done
+rm -f "$OUT"/examples/qtensor/*.pdf "$OUT"/examples/qtensor/src.*
 echo "$PKG" > "$OUT/home/.morphopackages"
 echo "$OBDIR" > "$OUT/openblas_dir.txt"
 echo "build_ref.sh: built $(ls "$OBJ"/*.o | wc -l) objects -> $OUT"

@@ -463,3 +463,67 @@ def test_reference_suite_passes_through_the_extension():
     ext = _run_reference_suite("import morphocuda", ["functionals"])       # 107 scripts, a CUDA context each
     assert ext["total"] >= 100
     assert ext["failed"] == [], ext["failed"]      # all of them pass on the stock build (oracle/refbuild/REF_TESTS.json)
+
+
+def _example(name, cut, tail, seed_random=False):
+    text = open(os.path.join(EXAMPLES, name, name + ".morpho")).read()
+    if cut in text:
+        text = text[:text.index(cut)]
+    for imp in ("import plot\n", "import povray\n", "import graphics\n"):
+        text = text.replace(imp, "")
+    if seed_random:          # random() is seeded from the clock: no two runs of the stock reference agree either
+        text = "var seed_ = 12345.0\nfn random(a) { seed_ = mod(seed_*16807.0, 2147483647.0); return seed_/2147483647.0 }\n" + text
+    return text + tail
+
+
+ENERGIES = '\nfor (en in problem.energies) print opt.total(en).format("%.15g")\n'
+MORE_EXAMPLES = [
+    # name, where the visualisation starts, what to print at the end, seeded random(), files beside the script, lines compared
+    ("qtensor", "// Define some helper functions to plot the result", ENERGIES, True, ["dense_disk.mesh"], 60, 1e-6),
+    ("cholesteric", "// Function to visualize a director field", ENERGIES, False, [], 60, 1e-6),
+    # ten rounds of "refine where the energy density exceeds 1.5 x the mean": a threshold on noisy numbers, the refined meshes
+    # of two runs differ in a few elements (174 / 172 printed lines) and the final energies in the sixth digit
+    ("electrostatics", "Show(plotmesh(mesh, grade=1))", ENERGIES, False, [], 60, 2e-4),
+    ("cube", "var g = plotmesh(m)", "", False, [], 40, 1e-6),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(EXAMPLES, "qtensor")), reason="oracle/_ref/examples not built")
+@pytest.mark.parametrize("ex", MORE_EXAMPLES, ids=[e[0] for e in MORE_EXAMPLES])
+def test_more_examples_as_shipped(tmp_path, ex):
+    """Shipped examples that live on the hot path, as shipped up to their visualisation block: examples/qtensor
+    (AreaIntegral of a Landau energy + LineIntegral anchoring with tangent() + GradSq, FieldOptimizer — the 2D sibling of
+    BASELINE config 5), examples/cholesteric (Nematic with pitch + LineIntegral + NormSq constraint), examples/electrostatics
+    (GradSq + LineIntegral penalties, ten adaptive refinements), examples/cube (Area at fixed VolumeEnclosed, four
+    refinement levels — the script behind config 2).  Every functional call runs on the GPU (no fallbacks); the printed
+    optimiser history agrees with the stock run to its six digits over the first lines and the final energies to 1e-6
+    (the optimisers amplify last-digit differences of finite-difference gradients from there on)."""
+    import shutil
+    name, cut, tail, seeded, files, nlines, ftol = ex
+    text = _example(name, cut, tail, seeded)
+    for f in files:
+        shutil.copy(os.path.join(EXAMPLES, name, f), tmp_path / f)
+    ref, _ = run(text, tmp_path, "stock.morpho")
+    new, err = run("import morphocuda\n" + text + "print cudastats()\n", tmp_path, "ext.morpho", {"MORPHO_CUDA_VERBOSE": "1"})
+    stats = [float(x) for x in NUM.findall(new[-1])]
+    print(name, "as shipped: cudastats", stats, "lines", len(ref), len(new) - 1)
+    assert stats[0] > 50 and stats[3] == 0, (stats, err[-1500:])
+    # the energy of every iteration (6 printed digits); `delta E` is a difference of nearly equal energies and the step
+    # size follows it, so those two columns carry the optimiser's own round-off and are not compared
+    en = re.compile(r"Energy: (\S+)")
+    # (the line search's "Cannot resolve bracket" remarks appear when three trial energies agree to all digits: noise)
+    ref_it = [l for l in ref if l.startswith("Iteration")][:nlines]
+    new_it = [l for l in new if l.startswith("Iteration")][:nlines]
+    assert len(ref_it) == len(new_it) and len(ref_it) >= min(nlines, 20), (len(ref_it), len(new_it))
+    for a, b in zip(ref_it, new_it):
+        x, y = float(en.search(a).group(1)), float(en.search(b).group(1))
+        assert abs(x - y) <= 2e-5 * max(abs(x), 1e-6), (name, a, b)
+    if tail:
+        k = len(ref) - 1 - [i for i, l in enumerate(ref) if l.startswith("Iteration")][-1]      # what is printed after the last iteration
+        assert k >= 1
+        for a, b in zip(ref[-k:], new[-1 - k:-1]):
+            if not NUM.findall(a) or a.startswith("Final mesh"):
+                continue
+            x, y = float(NUM.findall(a)[0]), float(NUM.findall(b)[0])
+            assert abs(x - y) <= ftol * max(abs(x), 1e-3), (name, a, b)
