@@ -148,13 +148,15 @@ def run_reference(args):
     nel = conn.shape[0]
     log(f"[reference] mesh f={f}: rank 0's {nel} of {part.nel_global} triangles built in {time.time() - t0:.1f}s")
     ncores = os.cpu_count() or 1
-    # calibrate on 1M triangles.  "All the host threads it can use": the reference's threaded map does not always
+    # calibrate on the whole mesh (up to 10M triangles: ~2 s per step and setting).  "All the host threads it can use": the reference's threaded map does not always
     # win (per-thread full gradient matrices + serial merge, functional.c:1092-1135), so keep the faster setting.
     def submesh(m):
         c = conn[:m]
         gids = np.unique(c)
         return np.ascontiguousarray(vert[gids]), np.ascontiguousarray(np.searchsorted(gids, c).astype(np.int32))
-    mcal = min(nel, 1_000_000)
+    # (on a sub-mesh large enough to be representative: the threaded map allocates one full-size gradient matrix per
+    #  thread and merges them serially, which wins at 1M triangles (26.7 against 14.9 M element-evals/s) and loses at 10M (10.3 against 13.8))
+    mcal = min(nel, 10_000_000)
     vcal, ccal = submesh(mcal)
     cal = {}
     for th in (0, ncores):
